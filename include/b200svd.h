@@ -1,0 +1,88 @@
+/* b200svd — C ABI of the B200-native StreamingSVD denoiser kernels (libb200svd.so).
+ *
+ * The reference (Picsart-AI-Research/StreamingT2V, pure Python) has no FFI: its seam for this path is the
+ * nn.Module call `StreamingWrapper.forward(x, t, c, **kwargs)` (code/models/diffusion/wrappers.py:23-78).  Every
+ * entry point below replaces one class of eager-PyTorch library calls that the reference makes underneath that
+ * seam; the citation on each function names the reference call sites it stands in for.  The Python host
+ * (streamingt2v_b200/) binds these with ctypes and mirrors the reference module interface.
+ *
+ * Conventions
+ *   - plain C: raw device pointers, integer sizes, a CUDA stream passed as void* (cudaStream_t).
+ *   - PyTorch (or any allocator) owns all memory; the library borrows pointers for the duration of a call.
+ *   - every function enqueues work on `stream` and returns without synchronising.
+ *   - return value 0 = success; non-zero = failure, message via b200svd_last_error() (thread local).
+ *   - activations are bf16, channel-last: [frames, H, W, C] == [(b t), (h w), c] token rows.
+ *   - no CPU fallback, no backend dispatch: sm_100a only.
+ */
+#ifndef B200SVD_H
+#define B200SVD_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200SVD_MAX_TAPS 12
+
+enum { B200SVD_ACT_NONE = 0, B200SVD_ACT_SILU = 1, B200SVD_ACT_GELU = 2, B200SVD_ACT_GEGLU = 3 };
+
+/* ---- library ------------------------------------------------------------------------------------------- */
+const char* b200svd_last_error(void);
+int b200svd_version(void);
+/* 0 if the current device is sm_100 and the driver entry points resolve, else error. */
+int b200svd_init(int device);
+
+/* ---- multi-tap tensor-core GEMM (tcgen05 + TMEM + TMA) --------------------------------------------------
+ * out[row, n] = s_acc * act( sum_{tap, k} A_tap[row, k] * W[tap, n, k] + bias[n] + fvec[row / rows_per_frame, n] )
+ *               + s1 * res1[row, n] + s2 * res2[row, n]
+ *
+ * One kernel covers: nn.Linear (attention.py:94-120, 262-351; video_attention.py; openaimodel.py emb_layers),
+ * 3x3 Conv2d stride 1/2 (openaimodel.py:107-207, 257-305), (3,1,1) Conv3d of the time_stack
+ * (video_model.py:46-59) — the A operand is addressed through a rank-5 TMA view of the channel-last activation,
+ * each tap is a coordinate offset in that view (out-of-bounds = zero padding), and all taps accumulate into one
+ * TMEM accumulator.  The epilogue carries the reference's elementwise neighbours: bias, per-frame embedding add
+ * (openaimodel.py:346-352), GEGLU (attention.py:94-101), residual adds and AlphaBlender (util.py:358-370).
+ */
+typedef struct {
+  /* A operand: bf16 tensor viewed as rank-5 (dim0 = channels, contiguous). strides in BYTES for dims 1..4. */
+  const void* a_ptr;
+  uint64_t a_dims[5];
+  uint64_t a_strides[4];
+  uint32_t a_box[5]; /* a_box[0] must be 64; product of a_box[1..4] must be 128 */
+  /* weights: bf16 [taps][n][k], k contiguous */
+  const void* w_ptr;
+  uint32_t n, k, taps;
+  int32_t tap_off[B200SVD_MAX_TAPS][5]; /* per-tap coordinate offset in the A view (dim0 = channel offset) */
+  /* output-pixel space (m1 fastest); boxes are powers of two with product 128 */
+  uint32_t m_ext[3];
+  uint32_t m_box[3];
+  uint32_t m_adim[3]; /* which A dim (1..4) each m dim walks */
+  /* output addressing: row = m1*out_rs[0] + m2*out_rs[1] + m3*out_rs[2]; element (row, col) at out + row*ldo + col */
+  int64_t out_rs[3];
+  void* out;
+  int64_t ldo;
+  int32_t out_fp32; /* 0: bf16 output, 1: fp32 output */
+  /* epilogue */
+  const float* bias;       /* [n] or NULL */
+  const float* fvec;       /* [frames][ldf] fp32 or NULL */
+  int64_t ldf;
+  uint32_t rows_per_frame; /* frame index = row / rows_per_frame */
+  int32_t act;             /* B200SVD_ACT_* ; GEGLU halves the output width (weights must be tile-interleaved) */
+  float s_acc;
+  const void* res1; /* bf16 [rows][ld1] or NULL */
+  int64_t ld1;
+  float s1;
+  const void* res2;
+  int64_t ld2;
+  float s2;
+  int32_t bn; /* N tile: 32, 64, 128 or 160 (0 = choose) */
+} b200svd_gemm_params;
+
+int b200svd_gemm(const b200svd_gemm_params* p, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SVD_H */

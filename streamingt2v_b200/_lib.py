@@ -1,0 +1,110 @@
+"""ctypes binding of libb200svd.so (the C-ABI boundary, include/b200svd.h).
+
+No torch types cross this boundary: tensors are passed as raw device pointers + sizes, the CUDA stream as a
+void*.  The library is mandatory — there is no CPU or eager-PyTorch fallback; a missing/unloadable library or a
+non-Blackwell device raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+_LIB = None
+LIB_PATH = Path(__file__).resolve().parent / "libb200svd.so"
+
+MAX_TAPS = 12
+ACT_NONE, ACT_SILU, ACT_GELU, ACT_GEGLU = 0, 1, 2, 3
+
+
+class GemmParams(C.Structure):
+    _fields_ = [
+        ("a_ptr", C.c_void_p),
+        ("a_dims", C.c_uint64 * 5),
+        ("a_strides", C.c_uint64 * 4),
+        ("a_box", C.c_uint32 * 5),
+        ("w_ptr", C.c_void_p),
+        ("n", C.c_uint32),
+        ("k", C.c_uint32),
+        ("taps", C.c_uint32),
+        ("tap_off", (C.c_int32 * 5) * MAX_TAPS),
+        ("m_ext", C.c_uint32 * 3),
+        ("m_box", C.c_uint32 * 3),
+        ("m_adim", C.c_uint32 * 3),
+        ("out_rs", C.c_int64 * 3),
+        ("out", C.c_void_p),
+        ("ldo", C.c_int64),
+        ("out_fp32", C.c_int32),
+        ("bias", C.c_void_p),
+        ("fvec", C.c_void_p),
+        ("ldf", C.c_int64),
+        ("rows_per_frame", C.c_uint32),
+        ("act", C.c_int32),
+        ("s_acc", C.c_float),
+        ("res1", C.c_void_p),
+        ("ld1", C.c_int64),
+        ("s1", C.c_float),
+        ("res2", C.c_void_p),
+        ("ld2", C.c_int64),
+        ("s2", C.c_float),
+        ("bn", C.c_int32),
+    ]
+
+
+class B200Error(RuntimeError):
+    pass
+
+
+def lib_path() -> Path:
+    return Path(os.environ.get("B200SVD_LIB", str(LIB_PATH)))
+
+
+def load():
+    """Load libb200svd.so (once) and declare the prototypes."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    p = lib_path()
+    if not p.exists():
+        raise B200Error(
+            f"{p} not found — build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is no fallback path)")
+    lib = C.CDLL(str(p))
+    lib.b200svd_last_error.restype = C.c_char_p
+    lib.b200svd_last_error.argtypes = []
+    lib.b200svd_version.restype = C.c_int
+    lib.b200svd_init.restype = C.c_int
+    lib.b200svd_init.argtypes = [C.c_int]
+    _declare(lib)
+    _LIB = lib
+    return lib
+
+
+# name -> argtypes; every entry returns int (0 = ok).  Kept in one table so the symbol-export test can walk it.
+PROTOTYPES = {
+    "b200svd_gemm": [C.POINTER(GemmParams), C.c_void_p],
+}
+
+
+def _declare(lib):
+    for name, argtypes in PROTOTYPES.items():
+        fn = getattr(lib, name)
+        fn.restype = C.c_int
+        fn.argtypes = argtypes
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = load().b200svd_last_error().decode("utf-8", "replace")
+        raise B200Error(f"{what}: {msg}" if what else msg)
+
+
+_inited = set()
+
+
+def init(device: int = 0):
+    if device in _inited:
+        return
+    lib = load()
+    check(lib.b200svd_init(int(device)), "b200svd_init")
+    _inited.add(device)

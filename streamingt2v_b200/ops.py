@@ -1,0 +1,193 @@
+"""Op-level host wrappers over the C ABI (ctypes): build the TMA views / tap tables and launch.
+
+All activations are bf16, channel-last ("(b t) h w c" == token rows "(b t) (h w) c").  Nothing here computes on
+the host; every function enqueues one hand-written sm_100a kernel on torch's current CUDA stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import itertools
+from functools import lru_cache
+
+import torch
+
+from . import _lib
+from ._lib import ACT_GEGLU, ACT_GELU, ACT_NONE, ACT_SILU, GemmParams
+
+_launch_count = 0
+
+
+def launches() -> int:
+    """Number of kernel launches issued through this module (bench.py's gpu_launches)."""
+    return _launch_count
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+@lru_cache(maxsize=None)
+def pick_box(e1: int, e2: int, e3: int):
+    """Power-of-two boxes (b1,b2,b3), b1*b2*b3 == 128, minimising the number of 128-row tiles over the
+    output-pixel space (e1,e2,e3); ties prefer the widest innermost box (longest contiguous TMA rows)."""
+    best = None
+    pows = [1, 2, 4, 8, 16, 32, 64, 128]
+    for b1, b2 in itertools.product(pows, pows):
+        if b1 * b2 > 128:
+            continue
+        b3 = 128 // (b1 * b2)
+        tiles = -(-e1 // b1) * -(-e2 // b2) * -(-e3 // b3)
+        key = (tiles, -b1, -b2)
+        if best is None or key < best[0]:
+            best = (key, (b1, b2, b3))
+    return best[1]
+
+
+def gemm_raw(*, a, a_dims, a_strides, a_box, w, n, k, taps, tap_off, m_ext, m_box, m_adim, out, ldo, out_rs=None,
+             out_fp32=False, bias=None, fvec=None, ldf=0, rows_per_frame=1, act=ACT_NONE, s_acc=1.0, res1=None,
+             ld1=0, s1=1.0, res2=None, ld2=0, s2=1.0, bn=0):
+    global _launch_count
+    p = GemmParams()
+    p.a_ptr = a.data_ptr()
+    for i in range(5):
+        p.a_dims[i] = int(a_dims[i])
+        p.a_box[i] = int(a_box[i])
+    for i in range(4):
+        p.a_strides[i] = int(a_strides[i])
+    p.w_ptr = w.data_ptr()
+    p.n, p.k, p.taps = int(n), int(k), int(taps)
+    for t in range(taps):
+        for i in range(5):
+            p.tap_off[t][i] = int(tap_off[t][i])
+    if out_rs is None:
+        out_rs = (1, m_ext[0], m_ext[0] * m_ext[1])
+    for i in range(3):
+        p.m_ext[i] = int(m_ext[i])
+        p.m_box[i] = int(m_box[i])
+        p.m_adim[i] = int(m_adim[i])
+        p.out_rs[i] = int(out_rs[i])
+    p.out = out.data_ptr()
+    p.ldo = int(ldo)
+    p.out_fp32 = 1 if out_fp32 else 0
+    p.bias = bias.data_ptr() if bias is not None else None
+    p.fvec = fvec.data_ptr() if fvec is not None else None
+    p.ldf = int(ldf)
+    p.rows_per_frame = int(rows_per_frame)
+    p.act = int(act)
+    p.s_acc = float(s_acc)
+    p.res1 = res1.data_ptr() if res1 is not None else None
+    p.ld1 = int(ld1)
+    p.s1 = float(s1)
+    p.res2 = res2.data_ptr() if res2 is not None else None
+    p.ld2 = int(ld2)
+    p.s2 = float(s2)
+    p.bn = int(bn)
+    lib = _lib.load()
+    _lib.check(lib.b200svd_gemm(C.byref(p), _stream()), "b200svd_gemm")
+    _launch_count += 1
+
+
+def _epi_kwargs(rows, n_out, out, bias, fvec, rows_per_frame, act, s_acc, res1, s1, res2, s2, out_fp32):
+    kw = dict(bias=bias, act=act, s_acc=s_acc, out_fp32=out_fp32)
+    if fvec is not None:
+        assert fvec.dtype == torch.float32 and fvec.stride(-1) == 1
+        kw.update(fvec=fvec, ldf=fvec.stride(0), rows_per_frame=rows_per_frame)
+    if res1 is not None:
+        assert res1.dtype == torch.bfloat16 and res1.stride(-1) == 1
+        kw.update(res1=res1, ld1=res1.stride(-2), s1=s1)
+    if res2 is not None:
+        assert res2.dtype == torch.bfloat16 and res2.stride(-1) == 1
+        kw.update(res2=res2, ld2=res2.stride(-2), s2=s2)
+    return kw
+
+
+def _alloc_out(rows, n_out, out, out_fp32, device):
+    if out is None:
+        out = torch.empty((rows, n_out), dtype=torch.float32 if out_fp32 else torch.bfloat16, device=device)
+    assert out.stride(-1) == 1
+    return out
+
+
+def linear(x, w, bias=None, *, act=ACT_NONE, out=None, out_fp32=False, fvec=None, rows_per_frame=1, s_acc=1.0,
+           res1=None, s1=1.0, res2=None, s2=1.0, bn=0):
+    """x: [M, K] bf16 (row stride arbitrary, multiple of 8); w: packed [1, N, K] bf16; returns [M, N_out]."""
+    assert x.dtype == torch.bfloat16 and x.dim() == 2 and x.stride(1) == 1
+    M, K = x.shape
+    N = w.shape[-2]
+    assert w.shape[-1] == K and w.is_contiguous()
+    n_out = N // 2 if act == ACT_GEGLU else N
+    out = _alloc_out(M, n_out, out, out_fp32, x.device)
+    ld = x.stride(0)
+    big = ld * 2 * max(M, 1)
+    gemm_raw(a=x, a_dims=(K, M, 1, 1, 1), a_strides=(ld * 2, big, big, big), a_box=(64, 128, 1, 1, 1),
+             w=w, n=N, k=K, taps=1, tap_off=[(0, 0, 0, 0, 0)], m_ext=(M, 1, 1), m_box=(128, 1, 1),
+             m_adim=(1, 2, 3), out=out, ldo=out.stride(0), bn=bn,
+             **_epi_kwargs(M, n_out, out, bias, fvec, rows_per_frame, act, s_acc, res1, s1, res2, s2, out_fp32))
+    return out
+
+
+def conv3x3(x, w, bias=None, *, out=None, **epi):
+    """x: [N, H, W, C] bf16 contiguous; w: packed [9, Cout, C] (tap = kh*3+kw); stride 1, zero pad 1.
+    Returns [N*H*W, Cout] rows (== [N, H, W, Cout])."""
+    assert x.dtype == torch.bfloat16 and x.dim() == 4 and x.is_contiguous()
+    N, H, W, Cc = x.shape
+    Cout = w.shape[1]
+    assert w.shape == (9, Cout, Cc) and w.is_contiguous()
+    b1, b2, b3 = pick_box(W, H, N)
+    taps = [(0, kw - 1, kh - 1, 0, 0) for kh in range(3) for kw in range(3)]
+    return _conv_common(x, (Cc, W, H, N, 1), (Cc * 2, W * Cc * 2, H * W * Cc * 2, N * H * W * Cc * 2),
+                        (64, b1, b2, b3, 1), w, Cout, Cc, taps, (W, H, N), (b1, b2, b3), (1, 2, 3), bias, out, epi)
+
+
+def conv3x3_s2(x, w, bias=None, *, out=None, **epi):
+    """Stride-2, pad-1 3x3 conv (Downsample.op, openaimodel.py:188-195).  x: [N, H, W, C] with even H, W.
+    The input is viewed as [N, H/2, 2, W/2, 2*C] so that every tap is a plain shifted TMA box."""
+    assert x.dtype == torch.bfloat16 and x.dim() == 4 and x.is_contiguous()
+    N, H, W, Cc = x.shape
+    assert H % 2 == 0 and W % 2 == 0
+    Ho, Wo = H // 2, W // 2
+    Cout = w.shape[1]
+    assert w.shape == (9, Cout, Cc) and w.is_contiguous()
+    b1, b2, b3 = pick_box(Wo, Ho, N)
+    taps = []
+    for kh in range(3):
+        dh, hp = ((-1, 1), (0, 0), (0, 1))[kh]
+        for kw in range(3):
+            dw, wp = ((-1, 1), (0, 0), (0, 1))[kw]
+            taps.append((wp * Cc, dw, hp, dh, 0))
+    return _conv_common(x, (2 * Cc, Wo, 2, Ho, N),
+                        (2 * Cc * 2, W * Cc * 2, 2 * W * Cc * 2, H * W * Cc * 2),
+                        (64, b1, 1, b2, b3), w, Cout, Cc, taps, (Wo, Ho, N), (b1, b2, b3), (1, 3, 4), bias, out, epi)
+
+
+def tconv3(x, w, bias=None, *, out=None, **epi):
+    """(3,1,1) temporal conv (time_stack ResBlock, video_model.py:46-59).  x: [B, T, P, C] bf16 contiguous
+    (P = H*W pixels); w: packed [3, Cout, C]; zero pad 1 along T.  Returns [B*T*P, Cout] rows."""
+    assert x.dtype == torch.bfloat16 and x.dim() == 4 and x.is_contiguous()
+    B, T, P, Cc = x.shape
+    Cout = w.shape[1]
+    assert w.shape == (3, Cout, Cc) and w.is_contiguous()
+    b1, b2, b3 = pick_box(P, T, B)
+    taps = [(0, 0, dt - 1, 0, 0) for dt in range(3)]
+    return _conv_common(x, (Cc, P, T, B, 1), (Cc * 2, P * Cc * 2, T * P * Cc * 2, B * T * P * Cc * 2),
+                        (64, b1, b2, b3, 1), w, Cout, Cc, taps, (P, T, B), (b1, b2, b3), (1, 2, 3), bias, out, epi)
+
+
+def _conv_common(x, a_dims, a_strides, a_box, w, Cout, K, taps, m_ext, m_box, m_adim, bias, out, epi):
+    rows = m_ext[0] * m_ext[1] * m_ext[2]
+    act = epi.pop("act", ACT_NONE)
+    out_fp32 = epi.pop("out_fp32", False)
+    bn = epi.pop("bn", 0)
+    n_out = Cout // 2 if act == ACT_GEGLU else Cout
+    out = _alloc_out(rows, n_out, out, out_fp32, x.device)
+    kw = _epi_kwargs(rows, n_out, out, bias, epi.pop("fvec", None), epi.pop("rows_per_frame", 1), act,
+                     epi.pop("s_acc", 1.0), epi.pop("res1", None), epi.pop("s1", 1.0), epi.pop("res2", None),
+                     epi.pop("s2", 1.0), out_fp32)
+    assert not epi, f"unknown epilogue args {list(epi)}"
+    gemm_raw(a=x, a_dims=a_dims, a_strides=a_strides, a_box=a_box, w=w, n=Cout, k=K, taps=len(taps), tap_off=taps,
+             m_ext=m_ext, m_box=m_box, m_adim=m_adim, out=out, ldo=out.stride(0), bn=bn, **kw)
+    return out

@@ -1,0 +1,114 @@
+"""GPU parity of the multi-tap tcgen05 GEMM (b200svd_gemm) against a plain PyTorch fp32 reference of the same op
+(floating-point kernel: bf16 operands, fp32 accumulate).  Tolerances: inputs are identical bf16 values on both
+sides, so the only differences are fp32 summation order and the final bf16 rounding of the output:
+|err| <= 2^-8 * |ref| + small abs (one bf16 ulp = 2^-8 relative)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(out, ref, name, rtol=2 ** -7, atol=2e-2):
+    out = out.float()
+    err = (out - ref).abs()
+    tol = atol + rtol * ref.abs()
+    bad = (err > tol).sum().item()
+    print(f"{name}: max_abs_err={err.max().item():.4e} ref_absmax={ref.abs().max().item():.3e} bad={bad}/{err.numel()}")
+    assert torch.isfinite(out).all(), f"{name}: non-finite output"
+    assert bad == 0, f"{name}: {bad} elements out of tolerance (max err {err.max().item():.4e})"
+
+
+def _rand(shape, dev, scale=1.0, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(dev).to(torch.bfloat16)
+
+
+@pytest.mark.parametrize("M,K,N,bn", [(256, 64, 32, 0), (300, 320, 320, 0), (1000, 320, 960, 0), (128, 1280, 1280, 128),
+                                      (777, 640, 640, 64), (50, 768, 1280, 0), (4096, 320, 320, 160)])
+def test_linear(cuda_dev, M, K, N, bn):
+    from streamingt2v_b200 import ops, packing
+    x = _rand((M, K), cuda_dev, seed=1)
+    w = _rand((N, K), cuda_dev, K ** -0.5, seed=2)
+    b = torch.randn(N, device=cuda_dev)
+    out = ops.linear(x, packing.pack_linear(w, cuda_dev), b, bn=bn)
+    torch.cuda.synchronize()
+    ref = x.float() @ w.float().t() + b
+    _check(out, ref, f"linear M{M} K{K} N{N} bn{bn}")
+
+
+def test_linear_epilogue(cuda_dev):
+    from streamingt2v_b200 import ops, packing
+    M, K, N, rpf = 640, 320, 320, 64
+    x = _rand((M, K), cuda_dev, seed=1)
+    w = _rand((N, K), cuda_dev, K ** -0.5, seed=2)
+    b = torch.randn(N, device=cuda_dev)
+    fvec = torch.randn(M // rpf, N, device=cuda_dev)
+    r1 = _rand((M, N), cuda_dev, seed=3)
+    r2 = _rand((M, N), cuda_dev, seed=4)
+    out = ops.linear(x, packing.pack_linear(w, cuda_dev), b, act=ops.ACT_SILU, fvec=fvec, rows_per_frame=rpf,
+                     s_acc=0.3, res1=r1, s1=0.7, res2=r2, s2=-0.5)
+    torch.cuda.synchronize()
+    v = x.float() @ w.float().t() + b + fvec.repeat_interleave(rpf, 0)
+    ref = 0.3 * F.silu(v) + 0.7 * r1.float() - 0.5 * r2.float()
+    _check(out, ref, "linear+epilogue")
+    out32 = ops.linear(x, packing.pack_linear(w, cuda_dev), b, out_fp32=True)
+    torch.cuda.synchronize()
+    _check(out32, x.float() @ w.float().t() + b, "linear fp32 out", rtol=1e-4, atol=1e-3)
+
+
+@pytest.mark.parametrize("K,F2", [(320, 2560), (64, 512), (128, 1024)])
+def test_geglu(cuda_dev, K, F2):
+    from streamingt2v_b200 import ops, packing
+    M = 500
+    x = _rand((M, K), cuda_dev, seed=1)
+    w = _rand((F2, K), cuda_dev, K ** -0.5, seed=2)
+    b = torch.randn(F2, device=cuda_dev) * 0.1
+    wp, bp, bn = packing.pack_geglu(w, b, cuda_dev)
+    out = ops.linear(x, wp, bp, act=ops.ACT_GEGLU, bn=bn)
+    torch.cuda.synchronize()
+    h = x.float() @ w.float().t() + b
+    a, g = h.chunk(2, dim=-1)
+    _check(out, a * F.gelu(g), f"geglu K{K} F2{F2}")
+
+
+@pytest.mark.parametrize("N,H,W,Cin,Cout", [(2, 8, 8, 64, 64), (3, 9, 16, 128, 64), (2, 18, 32, 320, 320),
+                                            (5, 4, 4, 64, 128), (16, 2, 2, 256, 256), (1, 72, 128, 64, 32),
+                                            (2, 16, 16, 8, 64), (2, 12, 20, 96, 96)])
+def test_conv3x3(cuda_dev, N, H, W, Cin, Cout):
+    from streamingt2v_b200 import ops, packing
+    x = _rand((N, H, W, Cin), cuda_dev, seed=1)
+    w = _rand((Cout, Cin, 3, 3), cuda_dev, (9 * Cin) ** -0.5, seed=2)
+    b = torch.randn(Cout, device=cuda_dev)
+    out = ops.conv3x3(x, packing.pack_conv3x3(w, cuda_dev), b)
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), b, padding=1).permute(0, 2, 3, 1).reshape(-1, Cout)
+    _check(out, ref, f"conv3x3 N{N} {H}x{W} {Cin}->{Cout}")
+
+
+@pytest.mark.parametrize("N,H,W,Cin,Cout", [(2, 8, 8, 64, 64), (3, 18, 32, 128, 128), (2, 72, 128, 32, 96),
+                                            (16, 4, 4, 64, 64), (1, 36, 64, 320, 320)])
+def test_conv3x3_s2(cuda_dev, N, H, W, Cin, Cout):
+    from streamingt2v_b200 import ops, packing
+    x = _rand((N, H, W, Cin), cuda_dev, seed=1)
+    w = _rand((Cout, Cin, 3, 3), cuda_dev, (9 * Cin) ** -0.5, seed=2)
+    b = torch.randn(Cout, device=cuda_dev)
+    out = ops.conv3x3_s2(x, packing.pack_conv3x3(w, cuda_dev), b)
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), b, padding=1, stride=2).permute(0, 2, 3, 1).reshape(-1, Cout)
+    _check(out, ref, f"conv3x3_s2 N{N} {H}x{W} {Cin}->{Cout}")
+
+
+@pytest.mark.parametrize("B,T,P,C", [(2, 8, 64, 64), (2, 25, 144, 128), (1, 7, 4, 256), (2, 25, 1024, 320)])
+def test_tconv3(cuda_dev, B, T, P, C):
+    from streamingt2v_b200 import ops, packing
+    x = _rand((B, T, P, C), cuda_dev, seed=1)
+    w = _rand((C, C, 3, 1, 1), cuda_dev, (3 * C) ** -0.5, seed=2)
+    b = torch.randn(C, device=cuda_dev)
+    r1 = _rand((B * T * P, C), cuda_dev, seed=5)
+    out = ops.tconv3(x, packing.pack_tconv3(w, cuda_dev), b, res1=r1, s1=1.0, s_acc=0.4)
+    torch.cuda.synchronize()
+    x5 = x.float().permute(0, 3, 1, 2)[..., None]  # b c t p 1
+    ref = F.conv3d(x5, w.float(), b, padding=(1, 0, 0))[..., 0].permute(0, 2, 3, 1).reshape(-1, C)
+    ref = 0.4 * ref + r1.float()
+    _check(out, ref, f"tconv3 B{B} T{T} P{P} C{C}")
