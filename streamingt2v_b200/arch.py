@@ -1,0 +1,310 @@
+"""Architecture plan of the StreamingSVD denoiser (VideoUNet + CAM mergers + ControlNet encoder).
+
+A pure-Python walk of the constructor loops of the reference
+(code/models/diffusion/video_model.py:94-495, code/models/control/controlnet.py:124-494) that yields
+ (a) the block plan — which sub-blocks exist under which state-dict prefix, with channel counts, and
+ (b) the parameter name -> shape grammar.
+The oracle (oracle/), the weight packer and the CUDA executor all consume this one description, so a mismatch
+with the reference's own `state_dict()` (pinned by oracle/make_golden.py) would show up everywhere at once.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Tuple
+
+
+@dataclass(frozen=True)
+class UNetConfig:
+    """Defaults = the shipped checkpoint config (reference code/config.yaml:69-115, :47-59)."""
+    in_channels: int = 8
+    model_channels: int = 320
+    out_channels: int = 4
+    num_res_blocks: int = 2
+    attention_resolutions: Tuple[int, ...] = (4, 2, 1)
+    channel_mult: Tuple[int, ...] = (1, 2, 4, 4)
+    num_head_channels: int = 64
+    context_dim: int = 1024
+    adm_in_channels: int = 768
+    use_apm: bool = False
+    apm_tokens: int = 17
+    # ControlNet conditioning embedding (config.yaml:54-59, use_image_encoder_normalization: true)
+    cond_embed_channels: Tuple[int, ...] = (32, 96, 256, 512)
+    cond_in_channels: int = 3
+    num_frame_conditioning: int = 7
+
+    @property
+    def time_embed_dim(self) -> int:
+        return self.model_channels * 4
+
+
+TINY = UNetConfig(model_channels=64, cond_embed_channels=(16, 32, 32, 64))
+"""Small same-topology config used for golden fixtures / fast parity tests (channels stay multiples of 64)."""
+
+
+@dataclass
+class Res:
+    prefix: str
+    cin: int
+    cout: int
+
+
+@dataclass
+class Attn:
+    prefix: str
+    ch: int
+
+    @property
+    def heads(self) -> int:
+        return self.ch // 64
+
+
+@dataclass
+class Down:
+    prefix: str  # "...N.0" ; conv at prefix + ".op"
+    ch: int
+
+
+@dataclass
+class Up:
+    prefix: str  # conv at prefix + ".conv"
+    ch: int
+
+
+@dataclass
+class Block:
+    """One TimestepEmbedSequential entry."""
+    layers: list = field(default_factory=list)
+    out_ch: int = 0
+    ds: int = 1  # spatial downsample factor of this block's OUTPUT
+
+
+@dataclass
+class Plan:
+    cfg: UNetConfig
+    input_blocks: List[Block]
+    middle: Block
+    output_blocks: List[Block]  # empty for the ControlNet
+    skip_chans: List[int]       # channels of hs[i] (input block outputs)
+
+
+def build_plan(cfg: UNetConfig, root: str, decoder: bool = True) -> Plan:
+    mc = cfg.model_channels
+    inb: List[Block] = [Block(layers=[("conv_in", f"{root}input_blocks.0.0")], out_ch=mc, ds=1)]
+    chans = [mc]
+    ch, ds = mc, 1
+    idx = 1
+    nl = len(cfg.channel_mult)
+    for level, mult in enumerate(cfg.channel_mult):
+        for _ in range(cfg.num_res_blocks):
+            layers = [Res(f"{root}input_blocks.{idx}.0", ch, mult * mc)]
+            ch = mult * mc
+            if ds in cfg.attention_resolutions:
+                layers.append(Attn(f"{root}input_blocks.{idx}.1", ch))
+            inb.append(Block(layers=layers, out_ch=ch, ds=ds))
+            chans.append(ch)
+            idx += 1
+        if level != nl - 1:
+            ds *= 2
+            inb.append(Block(layers=[Down(f"{root}input_blocks.{idx}.0", ch)], out_ch=ch, ds=ds))
+            chans.append(ch)
+            idx += 1
+    mid = Block(layers=[Res(f"{root}middle_block.0", ch, ch), Attn(f"{root}middle_block.1", ch),
+                        Res(f"{root}middle_block.2", ch, ch)], out_ch=ch, ds=ds)
+    outb: List[Block] = []
+    if decoder:
+        stack = list(chans)
+        oi = 0
+        for level, mult in list(enumerate(cfg.channel_mult))[::-1]:
+            for i in range(cfg.num_res_blocks + 1):
+                ich = stack.pop()
+                layers = [Res(f"{root}output_blocks.{oi}.0", ch + ich, mc * mult)]
+                ch = mc * mult
+                li = 1
+                if ds in cfg.attention_resolutions:
+                    layers.append(Attn(f"{root}output_blocks.{oi}.{li}", ch))
+                    li += 1
+                if level and i == cfg.num_res_blocks:
+                    ds //= 2
+                    layers.append(Up(f"{root}output_blocks.{oi}.{li}", ch))
+                outb.append(Block(layers=layers, out_ch=ch, ds=ds))
+                oi += 1
+    return Plan(cfg=cfg, input_blocks=inb, middle=mid, output_blocks=outb, skip_chans=chans)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# parameter grammar
+# --------------------------------------------------------------------------------------------------------------
+def _lin(d, p, cin, cout, bias=True):
+    d[p + ".weight"] = (cout, cin)
+    if bias:
+        d[p + ".bias"] = (cout,)
+
+
+def _norm(d, p, c):
+    d[p + ".weight"] = (c,)
+    d[p + ".bias"] = (c,)
+
+
+def _conv(d, p, cin, cout, k=3):
+    d[p + ".weight"] = (cout, cin, k, k)
+    d[p + ".bias"] = (cout,)
+
+
+def _res_shapes(d, p, cin, cout, temb):
+    _norm(d, p + ".in_layers.0", cin)
+    _conv(d, p + ".in_layers.2", cin, cout)
+    _lin(d, p + ".emb_layers.1", temb, cout)
+    _norm(d, p + ".out_layers.0", cout)
+    _conv(d, p + ".out_layers.3", cout, cout)
+    if cin != cout:
+        _conv(d, p + ".skip_connection", cin, cout, 1)
+    t = p + ".time_stack"
+    _norm(d, t + ".in_layers.0", cout)
+    d[t + ".in_layers.2.weight"] = (cout, cout, 3, 1, 1)
+    d[t + ".in_layers.2.bias"] = (cout,)
+    _lin(d, t + ".emb_layers.1", temb, cout)
+    _norm(d, t + ".out_layers.0", cout)
+    d[t + ".out_layers.3.weight"] = (cout, cout, 3, 1, 1)
+    d[t + ".out_layers.3.bias"] = (cout,)
+    d[p + ".time_mixer.mix_factor"] = (1,)
+
+
+def _xattn_shapes(d, p, c, ctx):
+    _lin(d, p + ".to_q", c, c, bias=False)
+    _lin(d, p + ".to_k", ctx, c, bias=False)
+    _lin(d, p + ".to_v", ctx, c, bias=False)
+    _lin(d, p + ".to_out.0", c, c)
+
+
+def _ff_shapes(d, p, c):
+    _lin(d, p + ".net.0.proj", c, 8 * c)
+    _lin(d, p + ".net.2", 4 * c, c)
+
+
+def _attn_shapes(d, p, c, cfg: UNetConfig):
+    _norm(d, p + ".norm", c)
+    _lin(d, p + ".proj_in", c, c)
+    b = p + ".transformer_blocks.0"
+    _xattn_shapes(d, b + ".attn1", c, c)
+    _ff_shapes(d, b + ".ff", c)
+    _xattn_shapes(d, b + ".attn2", c, cfg.context_dim)
+    for n in ("norm1", "norm2", "norm3"):
+        _norm(d, f"{b}.{n}", c)
+    if cfg.use_apm:
+        d[b + ".apm_conv.weight"] = (1, cfg.apm_tokens, 3)
+        d[b + ".apm_conv.bias"] = (1,)
+        _norm(d, b + ".apm_ln", cfg.context_dim)
+        d[b + ".apm_alpha"] = ()
+    _lin(d, p + ".proj_out", c, c)
+    t = p + ".time_stack.0"
+    _norm(d, t + ".norm_in", c)
+    _ff_shapes(d, t + ".ff_in", c)
+    _xattn_shapes(d, t + ".attn1", c, c)
+    _ff_shapes(d, t + ".ff", c)
+    _norm(d, t + ".norm2", c)
+    _xattn_shapes(d, t + ".attn2", c, cfg.context_dim)
+    _norm(d, t + ".norm1", c)
+    _norm(d, t + ".norm3", c)
+    _lin(d, p + ".time_pos_embed.0", c, 4 * c)
+    _lin(d, p + ".time_pos_embed.2", 4 * c, c)
+    d[p + ".time_mixer.mix_factor"] = (1,)
+
+
+def _cam_shapes(d, p, c):
+    t = p + ".temporal_transformer"
+    _lin(d, t + ".attention.to_q", c, c, bias=False)
+    _lin(d, t + ".attention.to_k", c, c, bias=False)
+    _lin(d, t + ".attention.to_v", c, c, bias=False)
+    _lin(d, t + ".attention.to_out.0", c, c)
+    _norm(d, t + ".norm", c)
+    _lin(d, t + ".proj_in", c, c)
+    _lin(d, t + ".proj_out", c, c)
+
+
+def _plan_shapes(d, plan: Plan, root: str):
+    cfg = plan.cfg
+    temb = cfg.time_embed_dim
+    _lin(d, root + "time_embed.0", cfg.model_channels, temb)
+    _lin(d, root + "time_embed.2", temb, temb)
+    _lin(d, root + "label_emb.0.0", cfg.adm_in_channels, temb)
+    _lin(d, root + "label_emb.0.2", temb, temb)
+    for blk in plan.input_blocks + [plan.middle] + plan.output_blocks:
+        for layer in blk.layers:
+            if isinstance(layer, tuple):
+                _conv(d, layer[1], cfg.in_channels, cfg.model_channels)
+            elif isinstance(layer, Res):
+                _res_shapes(d, layer.prefix, layer.cin, layer.cout, temb)
+            elif isinstance(layer, Attn):
+                _attn_shapes(d, layer.prefix, layer.ch, cfg)
+            elif isinstance(layer, Down):
+                _conv(d, layer.prefix + ".op", layer.ch, layer.ch)
+            elif isinstance(layer, Up):
+                _conv(d, layer.prefix + ".conv", layer.ch, layer.ch)
+
+
+def unet_param_shapes(cfg: UNetConfig, root: str = "") -> Dict[str, tuple]:
+    """Name -> shape of VideoUNet.state_dict() (controlnet_mode, attention_cross_attention merging)."""
+    d: Dict[str, tuple] = {}
+    plan = build_plan(cfg, root, decoder=True)
+    # registration order in the reference differs; only names/shapes matter
+    _plan_shapes(d, plan, root)
+    for i, c in enumerate(plan.skip_chans):
+        _cam_shapes(d, f"{root}cross_attention_merger_input_blocks.{i}", c)
+    _cam_shapes(d, f"{root}cross_attention_merger_mid_block", plan.middle.out_ch)
+    _norm(d, root + "out.0", cfg.model_channels)
+    _conv(d, root + "out.2", cfg.model_channels, cfg.out_channels)
+    return d
+
+
+def controlnet_param_shapes(cfg: UNetConfig, root: str = "") -> Dict[str, tuple]:
+    """Name -> shape of ControlNet.state_dict() (ControlNet.from_unet, use_image_encoder_normalization)."""
+    import dataclasses
+    d: Dict[str, tuple] = {}
+    ccfg = dataclasses.replace(cfg, use_apm=False)  # the ControlNet never uses APM (controlnet.py:176-199)
+    plan = build_plan(ccfg, root, decoder=False)
+    _plan_shapes(d, plan, root)
+    e = root + "controlnet_cond_embedding"
+    boc = cfg.cond_embed_channels
+    _conv(d, e + ".conv_in", cfg.cond_in_channels, boc[0])
+    bi = 0
+    for i in range(len(boc) - 1):
+        _conv(d, f"{e}.blocks.{bi}", boc[i], boc[i])
+        _norm(d, f"{e}.norms.{bi}", boc[i])
+        bi += 1
+        _conv(d, f"{e}.blocks.{bi}", boc[i], boc[i + 1])
+        _norm(d, f"{e}.norms.{bi}", boc[i + 1])
+        bi += 1
+    _conv(d, e + ".conv_out", boc[-1], cfg.model_channels)
+    return d
+
+
+def synth_state_dict(shapes: Dict[str, tuple], seed: int = 0):
+    """Deterministic synthetic weights, independent of module construction order: each tensor is drawn from a
+    numpy Generator seeded by (seed, crc32(name)).  Every tensor is non-zero — the reference zero-initialises
+    ResBlock out convs, transformer proj_out, UNet out conv, CAM proj_out and ControlNet conv_out
+    (openaimodel.py:296, attention.py:775-780, video_model.py:493, conditioning.py:113-114, controlnet.py:99-102),
+    which would make parity vacuous."""
+    import zlib
+
+    import numpy as np
+    import torch
+    sd = {}
+    for name in sorted(shapes):
+        shape = shapes[name]
+        rng = np.random.default_rng([seed, zlib.crc32(name.encode())])
+        leaf = name.rsplit(".", 1)[-1]
+        if name.endswith("mix_factor"):
+            v = rng.normal(0.0, 0.7, size=shape)
+        elif name.endswith("apm_alpha"):
+            v = np.asarray(0.6)
+        elif leaf == "weight" and len(shape) == 1:      # norm gains
+            v = 1.0 + 0.1 * rng.normal(size=shape)
+        elif leaf == "bias":
+            v = 0.05 * rng.normal(size=shape)
+        else:                                            # linear / conv weights: fan-in scaled
+            fan_in = 1
+            for s in shape[1:]:
+                fan_in *= s
+            v = rng.normal(size=shape) * (fan_in ** -0.5)
+        sd[name] = torch.from_numpy(np.asarray(v, dtype=np.float32).reshape(shape)).clone()
+    return sd
