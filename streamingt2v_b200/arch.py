@@ -37,8 +37,9 @@ class UNetConfig:
         return self.model_channels * 4
 
 
-TINY = UNetConfig(model_channels=64, cond_embed_channels=(16, 32, 32, 64))
-"""Small same-topology config used for golden fixtures / fast parity tests (channels stay multiples of 64)."""
+TINY = UNetConfig(channel_mult=(1, 1, 2, 2))
+"""Reduced same-topology config for golden fixtures / fast parity tests.  model_channels must stay 320: the
+reference hard-codes the ControlNet conditioning-embedding width to 320 (controlnet.py:443-447)."""
 
 
 @dataclass
@@ -274,7 +275,7 @@ def controlnet_param_shapes(cfg: UNetConfig, root: str = "") -> Dict[str, tuple]
         _conv(d, f"{e}.blocks.{bi}", boc[i], boc[i + 1])
         _norm(d, f"{e}.norms.{bi}", boc[i + 1])
         bi += 1
-    _conv(d, e + ".conv_out", boc[-1], cfg.model_channels)
+    _conv(d, e + ".conv_out", boc[-1], 320)  # hard-coded block_out_channels[0] (controlnet.py:443-447)
     return d
 
 
