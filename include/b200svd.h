@@ -82,6 +82,56 @@ typedef struct {
 
 int b200svd_gemm(const b200svd_gemm_params* p, void* stream);
 
+/* ---- FlashAttention forward, head dim 64 (tcgen05 + TMEM + TMA) -------------------------------------------
+ * Spatial self-attention core of BasicTransformerBlock.attn1 (attention.py:320-351 SDPA / :427-446 xformers).
+ * qkv: [(n s), ldqkv] bf16, columns [q | k | v] each heads*64 wide (output of the fused QKV projection);
+ * out: [(n s), ldo] bf16.  softmax(q k^T * scale) v per (frame, head). */
+int b200svd_flash_attn(const void* qkv, int64_t ldqkv, void* out, int64_t ldo, int n, int s, int heads, float scale,
+                       void* stream);
+
+/* ---- small-sequence attention, head dim 64, one warp per (batch, pixel, head) -----------------------------
+ * Temporal self-attention (video_attention.py:145-148), CAM cross-frame attention (cam/conditioning.py:65-68),
+ * temporal cross-attention over APM tokens (video_attention.py:150-154).  Row addressing:
+ *   q/out row(b,i,s) = (b*lq + i)*s_pixels + s ;  k/v row(b,j,s) = (b*lk + j)*s_pixels + s  (kv_per_pixel = 1)
+ *                                                  k/v row(b,j)   =  b*lk + j               (kv_per_pixel = 0) */
+int b200svd_small_attn(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o,
+                       int64_t ldo, int b, int s_pixels, int heads, int lq, int lk, int kv_per_pixel, float scale,
+                       void* stream);
+
+/* ---- GroupNorm(32) / LayerNorm, channel-last bf16, fp32 statistics ----------------------------------------
+ * GroupNorm32 (diffusionmodules/util.py:274-276), Normalize (attention.py:132-135), CAM joint norm over
+ * (C/32,F,H,W) (cam/conditioning.py:57-59: pass n = B, p = F*H*W), nn.LayerNorm (attention.py:528-530,
+ * video_attention.py:59-102, controlnet.py:113-118).
+ * x: [n][p][c] rows (stride ldx).  sums: n*32*2 doubles (sum, sum of squares), zeroed by gn_stats. */
+int b200svd_gn_stats(const void* x, int64_t ldx, int64_t n, int64_t p, int c, void* sums, void* stream);
+int b200svd_gn_apply(const void* x, int64_t ldx, void* y, int64_t ldy, int64_t n, int64_t p, int c, const void* sums,
+                     const float* gamma, const float* beta, float eps, int apply_silu, void* stream);
+/* y = LN(x [+ fvec[row / rows_per_frame]]) ; if xsum != NULL also writes xsum = bf16(x + fvec). */
+int b200svd_layernorm(const void* x, int64_t ldx, void* y, int64_t ldy, int64_t rows, int c, const float* gamma,
+                      const float* beta, float eps, const float* fvec, int64_t ldf, int rows_per_frame, void* xsum,
+                      int64_t ldxs, int apply_silu, void* stream);
+
+/* ---- layout / glue kernels ---------------------------------------------------------------------------------
+ * nchw_to_nhwc: wrappers.py:33 (cat of latents + concat cond) at the module seam; src [n][c_src][hw] fp32 with an
+ *   explicit frame stride -> dst[(n*hw + p)*ldd + c_off + c] bf16.
+ * nhwc_to_nchw: output of VideoUNet.out (video_model.py:618) back to [n][c][hw] fp32.
+ * upsample2x: Upsample nearest (openaimodel.py:138-155).  timestep_embed: util.py:207-231.
+ * add_silu: out = bf16(silu(a + b)) for emb = time_embed + label_emb followed by emb_layers' SiLU
+ *   (video_model.py:561-567, openaimodel.py:282-288).  add_rows: ControlNet Merger addition (controlnet.py:23-48).
+ * apm_mix: BasicTransformerBlockWithAPM context mix (attention.py:612-620). */
+int b200svd_nchw_to_nhwc(const float* src, int64_t src_frame_stride, int n, int c_src, int64_t hw, void* dst,
+                         int64_t ldd, int c_off, void* stream);
+int b200svd_nhwc_to_nchw(const void* src, int src_is_fp32, int64_t lds, int n, int c, int64_t hw, float* dst,
+                         void* stream);
+int b200svd_upsample2x(const void* x, void* y, int n, int h, int w, int c, void* stream);
+int b200svd_timestep_embed(const float* t, int n, int dim, float max_period, void* out, int64_t ldo, void* stream);
+int b200svd_add_silu(const float* a, const float* b, void* out, int64_t total, int apply_silu, void* stream);
+int b200svd_copy2d(const void* src, int64_t lds, void* dst, int64_t ldd, int64_t rows, int cols, void* stream);
+int b200svd_add_rows(void* dst, int64_t ldd, const void* src, int64_t lds, int64_t rows, int64_t src_rows, int cols,
+                     void* stream);
+int b200svd_apm_mix(const float* ctx, int n, int l, int d, const float* w, const float* wb, const float* ln_g,
+                    const float* ln_b, const float* alpha, void* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -81,8 +81,22 @@ def load():
 
 
 # name -> argtypes; every entry returns int (0 = ok).  Kept in one table so the symbol-export test can walk it.
+_P, _I64, _I, _F = C.c_void_p, C.c_int64, C.c_int, C.c_float
 PROTOTYPES = {
-    "b200svd_gemm": [C.POINTER(GemmParams), C.c_void_p],
+    "b200svd_gemm": [C.POINTER(GemmParams), _P],
+    "b200svd_flash_attn": [_P, _I64, _P, _I64, _I, _I, _I, _F, _P],
+    "b200svd_small_attn": [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _I, _I, _I, _I, _I, _I, _F, _P],
+    "b200svd_gn_stats": [_P, _I64, _I64, _I64, _I, _P, _P],
+    "b200svd_gn_apply": [_P, _I64, _P, _I64, _I64, _I64, _I, _P, _P, _P, _F, _I, _P],
+    "b200svd_layernorm": [_P, _I64, _P, _I64, _I64, _I, _P, _P, _F, _P, _I64, _I, _P, _I64, _I, _P],
+    "b200svd_nchw_to_nhwc": [_P, _I64, _I, _I, _I64, _P, _I64, _I, _P],
+    "b200svd_nhwc_to_nchw": [_P, _I, _I64, _I, _I, _I64, _P, _P],
+    "b200svd_upsample2x": [_P, _P, _I, _I, _I, _I, _P],
+    "b200svd_timestep_embed": [_P, _I, _I, _F, _P, _I64, _P],
+    "b200svd_add_silu": [_P, _P, _P, _I64, _I, _P],
+    "b200svd_copy2d": [_P, _I64, _P, _I64, _I64, _I, _P],
+    "b200svd_add_rows": [_P, _I64, _P, _I64, _I64, _I64, _I, _P],
+    "b200svd_apm_mix": [_P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P],
 }
 
 

@@ -1,0 +1,291 @@
+// GroupNorm (32 groups, channel-last) and LayerNorm kernels — HBM-bound, 16-byte vectorised, fp32 statistics.
+//
+// Replaces: GroupNorm32 (reference code/models/svd/sgm/modules/diffusionmodules/util.py:274-276, eps 1e-5),
+// Normalize (attention.py:132-135, eps 1e-6), the CAM joint (C/32,F,H,W) GroupNorm (code/models/cam/conditioning.py:57-59),
+// nn.LayerNorm (attention.py:528-530, video_attention.py:59,87,101-102; controlnet.py:113-118).
+#include <cuda_bf16.h>
+
+#include "../../include/b200svd.h"
+#include "common.h"
+#include "ptx.cuh"
+
+namespace b200 {
+
+// ------------------------------------------------------------------------------------------------------------
+// GroupNorm statistics: x [N][P][C] bf16 (row stride ldx) -> sums [N][32][2] (double: sum, sum of squares).
+// grid = (chunks, N); block = (C/8) * rows_per_iter threads; each thread owns one 8-channel vector column.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, int P, int C, int rows_per_chunk,
+                                double* __restrict__ sums) {
+  extern __shared__ float sm[];  // [2][C]
+  const int vecs = C >> 3;
+  const int n = blockIdx.y;
+  const int p0 = blockIdx.x * rows_per_chunk;
+  const int p1 = min(P, p0 + rows_per_chunk);
+  const int v = threadIdx.x % vecs;
+  const int r0 = threadIdx.x / vecs;
+  const int rstep = blockDim.x / vecs;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
+  __syncthreads();
+  float s[8], q[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+  const __nv_bfloat16* base = x + ((int64_t)n * P) * ldx + v * 8;
+  for (int p = p0 + r0; p < p1; p += rstep) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(base + (int64_t)p * ldx));
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float a = bf16_lo(w[j]), b = bf16_hi(w[j]);
+      s[2 * j] += a;
+      q[2 * j] += a * a;
+      s[2 * j + 1] += b;
+      q[2 * j + 1] += b * b;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    atomicAdd(&sm[v * 8 + j], s[j]);
+    atomicAdd(&sm[C + v * 8 + j], q[j]);
+  }
+  __syncthreads();
+  const int cpg = C >> 5;
+  if (threadIdx.x < 32) {
+    double a = 0.0, b = 0.0;
+    for (int j = 0; j < cpg; ++j) {
+      a += (double)sm[threadIdx.x * cpg + j];
+      b += (double)sm[C + threadIdx.x * cpg + j];
+    }
+    atomicAdd(&sums[((int64_t)n * 32 + threadIdx.x) * 2], a);
+    atomicAdd(&sums[((int64_t)n * 32 + threadIdx.x) * 2 + 1], b);
+  }
+}
+
+// y = [silu]((x - mean) * rstd * gamma + beta), bf16 out (row stride ldy).
+__global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, __nv_bfloat16* __restrict__ y,
+                                int64_t ldy, int P, int C, int rows_per_chunk, const double* __restrict__ sums,
+                                const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                int apply_silu) {
+  const int vecs = C >> 3;
+  const int n = blockIdx.y;
+  const int p0 = blockIdx.x * rows_per_chunk;
+  const int p1 = min(P, p0 + rows_per_chunk);
+  const int v = threadIdx.x % vecs;
+  const int r0 = threadIdx.x / vecs;
+  const int rstep = blockDim.x / vecs;
+  const int cpg = C >> 5;
+  const double cnt = (double)P * (double)cpg;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = v * 8 + j;
+    const int g = c / cpg;
+    const double su = sums[((int64_t)n * 32 + g) * 2], sq = sums[((int64_t)n * 32 + g) * 2 + 1];
+    const double mean = su / cnt;
+    double var = sq / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float ga = __ldg(gamma + c), be = __ldg(beta + c);
+    sc[j] = rstd * ga;
+    sh[j] = be - (float)mean * rstd * ga;
+  }
+  const __nv_bfloat16* xb = x + ((int64_t)n * P) * ldx + v * 8;
+  __nv_bfloat16* yb = y + ((int64_t)n * P) * ldy + v * 8;
+  for (int p = p0 + r0; p < p1; p += rstep) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(xb + (int64_t)p * ldx));
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float a = bf16_lo(w[j]) * sc[2 * j] + sh[2 * j];
+      float b = bf16_hi(w[j]) * sc[2 * j + 1] + sh[2 * j + 1];
+      if (apply_silu) {
+        a = silu_f(a);
+        b = silu_f(b);
+      }
+      o[j] = pack_bf16x2(a, b);
+    }
+    *reinterpret_cast<uint4*>(yb + (int64_t)p * ldy) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// LayerNorm over the channel dim: one warp per row.  y = ((x [+ fvec[row/rpf]]) - mean) * rstd * gamma + beta
+// Optional: also write xsum = x + fvec (bf16) so the caller can use it as the residual stream, and fused SiLU.
+// ------------------------------------------------------------------------------------------------------------
+template <int MAXV>  // max 8-channel vectors per lane
+__global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, __nv_bfloat16* __restrict__ y,
+                                 int64_t ldy, int64_t rows, int C, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, float eps, const float* __restrict__ fvec, int64_t ldf,
+                                 int rows_per_frame, __nv_bfloat16* __restrict__ xsum, int64_t ldxs, int apply_silu) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int vecs = C >> 3;
+  float val[MAXV][8];
+  const __nv_bfloat16* xr = x + row * ldx;
+  const float* fr = fvec ? fvec + (row / rows_per_frame) * ldf : nullptr;
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int v = lane + i * 32;
+    if (v < vecs) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(xr + v * 8));
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        val[i][2 * j] = bf16_lo(w[j]);
+        val[i][2 * j + 1] = bf16_hi(w[j]);
+      }
+      if (fr) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) val[i][j] += __ldg(fr + v * 8 + j);
+        if (xsum) {
+          uint32_t o[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) o[j] = pack_bf16x2(val[i][2 * j], val[i][2 * j + 1]);
+          *reinterpret_cast<uint4*>(xsum + row * ldxs + v * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+          // the residual stream is the bf16-rounded sum; normalise exactly what the consumer will see
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            val[i][2 * j] = bf16_lo(o[j]);
+            val[i][2 * j + 1] = bf16_hi(o[j]);
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sum += val[i][j];
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / (float)C;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int v = lane + i * 32;
+    if (v < vecs) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = val[i][j] - mean;
+        sq += d * d;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  const float rstd = rsqrtf(sq / (float)C + eps);
+  __nv_bfloat16* yr = y + row * ldy;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int v = lane + i * 32;
+    if (v < vecs) {
+      float o8[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = v * 8 + j;
+        float t = (val[i][j] - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c);
+        if (apply_silu) t = silu_f(t);
+        o8[j] = t;
+      }
+      *reinterpret_cast<uint4*>(yr + v * 8) = make_uint4(pack_bf16x2(o8[0], o8[1]), pack_bf16x2(o8[2], o8[3]),
+                                                          pack_bf16x2(o8[4], o8[5]), pack_bf16x2(o8[6], o8[7]));
+    }
+  }
+}
+
+static int gn_geometry(int C, int P, int* threads, int* rows_per_chunk, int* chunks) {
+  if (C % 8 != 0 || C % 32 != 0) return 1;
+  const int vecs = C / 8;
+  if (vecs > 1024) return 1;
+  int rpi = 256 / vecs;
+  if (rpi < 1) rpi = 1;
+  *threads = vecs * rpi;
+  // ~2 waves of CTAs over the GPU per sample batch is plenty; keep chunks >= 64 rows
+  int rpc = 256;
+  if (P < rpc) rpc = P;
+  *rows_per_chunk = rpc;
+  *chunks = (P + rpc - 1) / rpc;
+  return 0;
+}
+
+}  // namespace b200
+
+extern "C" {
+
+// sums must hold N*32*2 doubles; it is zeroed here (memsetAsync) before accumulation.
+int b200svd_gn_stats(const void* x, int64_t ldx, int64_t n, int64_t p, int c, void* sums, void* stream) {
+  using namespace b200;
+  int threads, rpc, chunks;
+  if (gn_geometry(c, (int)p, &threads, &rpc, &chunks)) {
+    set_error("gn_stats: unsupported channel count %d (need multiple of 32, <= 8192)", c);
+    return 1;
+  }
+  if (ldx % 8 != 0) {
+    set_error("gn_stats: ldx must be a multiple of 8");
+    return 1;
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  cudaError_t e = cudaMemsetAsync(sums, 0, (size_t)n * 32 * 2 * sizeof(double), st);
+  if (e != cudaSuccess) return cuda_fail(e, "gn_stats memset");
+  dim3 grid(chunks, (unsigned)n);
+  gn_stats_kernel<<<grid, threads, 2 * c * sizeof(float), st>>>(reinterpret_cast<const __nv_bfloat16*>(x), ldx, (int)p,
+                                                               c, rpc, reinterpret_cast<double*>(sums));
+  B200_CHECK_LAUNCH("gn_stats");
+  return 0;
+}
+
+int b200svd_gn_apply(const void* x, int64_t ldx, void* y, int64_t ldy, int64_t n, int64_t p, int c, const void* sums,
+                     const float* gamma, const float* beta, float eps, int apply_silu, void* stream) {
+  using namespace b200;
+  int threads, rpc, chunks;
+  if (gn_geometry(c, (int)p, &threads, &rpc, &chunks)) {
+    set_error("gn_apply: unsupported channel count %d", c);
+    return 1;
+  }
+  if (ldx % 8 != 0 || ldy % 8 != 0) {
+    set_error("gn_apply: leading dims must be multiples of 8");
+    return 1;
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  dim3 grid(chunks, (unsigned)n);
+  gn_apply_kernel<<<grid, threads, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), ldx,
+                                            reinterpret_cast<__nv_bfloat16*>(y), ldy, (int)p, c, rpc,
+                                            reinterpret_cast<const double*>(sums), gamma, beta, eps, apply_silu);
+  B200_CHECK_LAUNCH("gn_apply");
+  return 0;
+}
+
+int b200svd_layernorm(const void* x, int64_t ldx, void* y, int64_t ldy, int64_t rows, int c, const float* gamma,
+                      const float* beta, float eps, const float* fvec, int64_t ldf, int rows_per_frame, void* xsum,
+                      int64_t ldxs, int apply_silu, void* stream) {
+  using namespace b200;
+  if (c % 8 != 0 || c > 8 * 32 * 8) {
+    set_error("layernorm: unsupported width %d (multiple of 8, <= 2048)", c);
+    return 1;
+  }
+  if (ldx % 8 != 0 || ldy % 8 != 0 || (xsum && ldxs % 8 != 0)) {
+    set_error("layernorm: leading dims must be multiples of 8");
+    return 1;
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int wpb = 8;
+  const unsigned grid = (unsigned)((rows + wpb - 1) / wpb);
+  const int vecs = c / 8;
+  const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(x);
+  __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(y);
+  __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(xsum);
+  if (rows_per_frame <= 0) rows_per_frame = 1;
+#define LN_LAUNCH(MV)                                                                                              \
+  layernorm_kernel<MV><<<grid, wpb * 32, 0, st>>>(xp, ldx, yp, ldy, rows, c, gamma, beta, eps, fvec, ldf,          \
+                                                  rows_per_frame, xs, ldxs, apply_silu)
+  if (vecs <= 32) LN_LAUNCH(1);
+  else if (vecs <= 64) LN_LAUNCH(2);
+  else if (vecs <= 128) LN_LAUNCH(4);
+  else LN_LAUNCH(8);
+#undef LN_LAUNCH
+  B200_CHECK_LAUNCH("layernorm");
+  return 0;
+}
+
+}  // extern "C"

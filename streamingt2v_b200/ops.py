@@ -191,3 +191,129 @@ def _conv_common(x, a_dims, a_strides, a_box, w, Cout, K, taps, m_ext, m_box, m_
     gemm_raw(a=x, a_dims=a_dims, a_strides=a_strides, a_box=a_box, w=w, n=Cout, k=K, taps=len(taps), tap_off=taps,
              m_ext=m_ext, m_box=m_box, m_adim=m_adim, out=out, ldo=out.stride(0), bn=bn, **kw)
     return out
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# attention
+# ----------------------------------------------------------------------------------------------------------------
+def _call(name, *args):
+    global _launch_count
+    lib = _lib.load()
+    _lib.check(getattr(lib, name)(*args), name)
+    _launch_count += 1
+
+
+def flash_attn(qkv, n, s, heads, out=None):
+    """qkv: [(n s), 3*heads*64] bf16 (row stride free) -> [(n s), heads*64]."""
+    assert qkv.dtype == torch.bfloat16 and qkv.dim() == 2 and qkv.stride(1) == 1
+    Cc = heads * 64
+    assert qkv.shape == (n * s, 3 * Cc)
+    if out is None:
+        out = torch.empty((n * s, Cc), dtype=torch.bfloat16, device=qkv.device)
+    _call("b200svd_flash_attn", _ptr(qkv), qkv.stride(0), _ptr(out), out.stride(0), n, s, heads, 64 ** -0.5, _stream())
+    return out
+
+
+def small_attn(q, k, v, *, b, s, heads, lq, lk, kv_per_pixel=True, out=None):
+    """q: rows (b, i<lq, s); k, v: rows (b, j<lk, s) or (b, j) when kv_per_pixel=False; head dim 64."""
+    for t in (q, k, v):
+        assert t.dtype == torch.bfloat16 and t.dim() == 2 and t.stride(1) == 1
+    Cc = heads * 64
+    if out is None:
+        out = torch.empty((b * lq * s, Cc), dtype=torch.bfloat16, device=q.device)
+    _call("b200svd_small_attn", _ptr(q), q.stride(0), _ptr(k), k.stride(0), _ptr(v), v.stride(0), _ptr(out),
+          out.stride(0), b, s, heads, lq, lk, 1 if kv_per_pixel else 0, 64 ** -0.5, _stream())
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# norms
+# ----------------------------------------------------------------------------------------------------------------
+def group_norm(x, n, p, gamma, beta, eps, *, silu=False, out=None, sums=None):
+    """x: [(n p), C] bf16 rows; 32 groups; statistics over (p, C/32) per sample n.  Returns bf16 [(n p), C]."""
+    assert x.dtype == torch.bfloat16 and x.dim() == 2 and x.stride(1) == 1 and x.shape[0] == n * p
+    Cc = x.shape[1]
+    if sums is None:
+        sums = torch.empty((n, 32, 2), dtype=torch.float64, device=x.device)
+    if out is None:
+        out = torch.empty((n * p, Cc), dtype=torch.bfloat16, device=x.device)
+    _call("b200svd_gn_stats", _ptr(x), x.stride(0), n, p, Cc, _ptr(sums), _stream())
+    _call("b200svd_gn_apply", _ptr(x), x.stride(0), _ptr(out), out.stride(0), n, p, Cc, _ptr(sums), _ptr(gamma),
+          _ptr(beta), float(eps), 1 if silu else 0, _stream())
+    return out
+
+
+def layer_norm(x, gamma, beta, eps=1e-5, *, fvec=None, rows_per_frame=1, xsum=None, silu=False, out=None):
+    assert x.dtype == torch.bfloat16 and x.dim() == 2 and x.stride(1) == 1
+    rows, Cc = x.shape
+    if out is None:
+        out = torch.empty((rows, Cc), dtype=torch.bfloat16, device=x.device)
+    _call("b200svd_layernorm", _ptr(x), x.stride(0), _ptr(out), out.stride(0), rows, Cc, _ptr(gamma), _ptr(beta),
+          float(eps), _ptr(fvec), fvec.stride(0) if fvec is not None else 0, rows_per_frame, _ptr(xsum),
+          xsum.stride(0) if xsum is not None else 0, 1 if silu else 0, _stream())
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# glue
+# ----------------------------------------------------------------------------------------------------------------
+def nchw_to_nhwc(src, dst, c_off=0):
+    """src [N, C, H, W] fp32 (frame stride free, CHW contiguous) -> dst rows [(N H W), ld] bf16 at column c_off."""
+    assert src.dtype == torch.float32 and src.dim() == 4
+    N, Cs, H, W = src.shape
+    assert src.stride(3) == 1 and src.stride(2) == W and src.stride(1) == H * W
+    _call("b200svd_nchw_to_nhwc", _ptr(src), src.stride(0), N, Cs, H * W, _ptr(dst), dst.stride(0), c_off, _stream())
+    return dst
+
+
+def nhwc_to_nchw(src, n, c, hw, out):
+    assert out.dtype == torch.float32 and out.is_contiguous()
+    _call("b200svd_nhwc_to_nchw", _ptr(src), 1 if src.dtype == torch.float32 else 0, src.stride(0), n, c, hw, _ptr(out),
+          _stream())
+    return out
+
+
+def upsample2x(x, n, h, w):
+    """x: [(n h w), C] bf16 contiguous -> [(n 2h 2w), C]."""
+    assert x.dtype == torch.bfloat16 and x.is_contiguous()
+    Cc = x.shape[-1]
+    y = torch.empty((n * 4 * h * w, Cc), dtype=torch.bfloat16, device=x.device)
+    _call("b200svd_upsample2x", _ptr(x), _ptr(y), n, h, w, Cc, _stream())
+    return y
+
+
+def timestep_embed(t, dim, max_period=10000.0):
+    assert t.dtype == torch.float32 and t.is_contiguous()
+    out = torch.empty((t.numel(), dim), dtype=torch.bfloat16, device=t.device)
+    _call("b200svd_timestep_embed", _ptr(t), t.numel(), dim, float(max_period), _ptr(out), out.stride(0), _stream())
+    return out
+
+
+def add_silu(a, b=None, silu=True):
+    assert a.dtype == torch.float32 and a.is_contiguous() and (b is None or (b.is_contiguous() and b.shape == a.shape))
+    out = torch.empty(a.shape, dtype=torch.bfloat16, device=a.device)
+    _call("b200svd_add_silu", _ptr(a), _ptr(b), _ptr(out), a.numel(), 1 if silu else 0, _stream())
+    return out
+
+
+def copy2d(src, dst):
+    assert src.shape == dst.shape and src.dim() == 2
+    _call("b200svd_copy2d", _ptr(src), src.stride(0), _ptr(dst), dst.stride(0), src.shape[0], src.shape[1], _stream())
+    return dst
+
+
+def add_rows(dst, src):
+    """dst[r] += src[r % src_rows] (bf16, in place)."""
+    _call("b200svd_add_rows", _ptr(dst), dst.stride(0), _ptr(src), src.stride(0), dst.shape[0], src.shape[0],
+          dst.shape[1], _stream())
+    return dst
+
+
+def apm_mix(ctx, w, wb, ln_g, ln_b, alpha):
+    """ctx [N, L, D] fp32 -> [N, D] bf16 (attention.py:612-620)."""
+    assert ctx.dtype == torch.float32 and ctx.is_contiguous()
+    N, L, D = ctx.shape
+    out = torch.empty((N, D), dtype=torch.bfloat16, device=ctx.device)
+    _call("b200svd_apm_mix", _ptr(ctx), N, L, D, _ptr(w), _ptr(wb), _ptr(ln_g), _ptr(ln_b), _ptr(alpha), _ptr(out),
+          _stream())
+    return out
