@@ -102,8 +102,12 @@ int b200svd_small_attn(const void* q, int64_t ldq, const void* k, int64_t ldk, c
  * GroupNorm32 (diffusionmodules/util.py:274-276), Normalize (attention.py:132-135), CAM joint norm over
  * (C/32,F,H,W) (cam/conditioning.py:57-59: pass n = B, p = F*H*W), nn.LayerNorm (attention.py:528-530,
  * video_attention.py:59-102, controlnet.py:113-118).
- * x: [n][p][c] rows (stride ldx).  sums: n*32*2 doubles (sum, sum of squares), zeroed by gn_stats. */
-int b200svd_gn_stats(const void* x, int64_t ldx, int64_t n, int64_t p, int c, void* sums, void* stream);
+ * x: [n][p][c] rows (stride ldx).  sums: n*32*2 doubles (sum, sum of squares).  The reduction is deterministic
+ * (fixed order, no floating-point atomics): scratch holds per-chunk partials (b200svd_gn_scratch_doubles doubles),
+ * counters is n int32 zero-initialised once by the caller (left zero by every call). */
+int64_t b200svd_gn_scratch_doubles(int64_t n, int64_t p, int c);
+int b200svd_gn_stats(const void* x, int64_t ldx, int64_t n, int64_t p, int c, void* sums, void* scratch,
+                     void* counters, void* stream);
 int b200svd_gn_apply(const void* x, int64_t ldx, void* y, int64_t ldy, int64_t n, int64_t p, int c, const void* sums,
                      const float* gamma, const float* beta, float eps, int apply_silu, void* stream);
 /* y = LN(x [+ fvec[row / rows_per_frame]]) ; if xsum != NULL also writes xsum = bf16(x + fvec). */

@@ -76,6 +76,8 @@ def load():
     lib.b200svd_init.restype = C.c_int
     lib.b200svd_init.argtypes = [C.c_int]
     _declare(lib)
+    lib.b200svd_gn_scratch_doubles.restype = C.c_int64
+    lib.b200svd_gn_scratch_doubles.argtypes = [C.c_int64, C.c_int64, C.c_int]
     _LIB = lib
     return lib
 
@@ -86,7 +88,7 @@ PROTOTYPES = {
     "b200svd_gemm": [C.POINTER(GemmParams), _P],
     "b200svd_flash_attn": [_P, _I64, _P, _I64, _I, _I, _I, _F, _P],
     "b200svd_small_attn": [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _I, _I, _I, _I, _I, _I, _F, _P],
-    "b200svd_gn_stats": [_P, _I64, _I64, _I64, _I, _P, _P],
+    "b200svd_gn_stats": [_P, _I64, _I64, _I64, _I, _P, _P, _P, _P],
     "b200svd_gn_apply": [_P, _I64, _P, _I64, _I64, _I64, _I, _P, _P, _P, _F, _I, _P],
     "b200svd_layernorm": [_P, _I64, _P, _I64, _I64, _I, _P, _P, _F, _P, _I64, _I, _P, _I64, _I, _P],
     "b200svd_nchw_to_nhwc": [_P, _I64, _I, _I, _I64, _P, _I64, _I, _P],

@@ -309,3 +309,30 @@ def synth_state_dict(shapes: Dict[str, tuple], seed: int = 0):
             v = rng.normal(size=shape) * (fan_in ** -0.5)
         sd[name] = torch.from_numpy(np.asarray(v, dtype=np.float32).reshape(shape)).clone()
     return sd
+
+
+def synth_state_dict_device(shapes: Dict[str, tuple], device, seed: int = 0):
+    """Fast on-device variant of synth_state_dict for full-size benchmarks (same distribution family, values not
+    reproducible across devices — use synth_state_dict wherever outputs are compared)."""
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    sd = {}
+    for name in sorted(shapes):
+        shape = shapes[name]
+        leaf = name.rsplit(".", 1)[-1]
+        if name.endswith("mix_factor"):
+            v = torch.randn(shape, generator=g, device=device) * 0.7
+        elif name.endswith("apm_alpha"):
+            v = torch.tensor(0.6, device=device)
+        elif leaf == "weight" and len(shape) == 1:
+            v = 1.0 + 0.1 * torch.randn(shape, generator=g, device=device)
+        elif leaf == "bias":
+            v = 0.05 * torch.randn(shape, generator=g, device=device)
+        else:
+            fan_in = 1
+            for s in shape[1:]:
+                fan_in *= s
+            v = torch.randn(shape, generator=g, device=device) * (fan_in ** -0.5)
+        sd[name] = v
+    return sd

@@ -16,17 +16,21 @@ namespace b200 {
 // grid = (chunks, N); block = (C/8) * rows_per_iter threads; each thread owns one 8-channel vector column.
 // ------------------------------------------------------------------------------------------------------------
 __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, int P, int C, int rows_per_chunk,
-                                double* __restrict__ sums) {
-  extern __shared__ float sm[];  // [2][C]
+                                double* __restrict__ sums, double* __restrict__ partial, int* __restrict__ counters) {
+  // Deterministic (fixed summation order, no floating-point atomics):
+  //   thread partials -> smem [rstep][2C] -> per-channel sums (fixed order over rstep) -> per-group chunk partial
+  //   (double) -> global partial[n][chunk][64]; the LAST chunk block of sample n (atomic ticket) adds all chunk
+  //   partials in chunk order and writes sums[n][32][2].
+  extern __shared__ float sm[];  // [rstep][2][C]
+  __shared__ int is_last;
   const int vecs = C >> 3;
   const int n = blockIdx.y;
+  const int chunks = gridDim.x;
   const int p0 = blockIdx.x * rows_per_chunk;
   const int p1 = min(P, p0 + rows_per_chunk);
   const int v = threadIdx.x % vecs;
   const int r0 = threadIdx.x / vecs;
   const int rstep = blockDim.x / vecs;
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
-  __syncthreads();
   float s[8], q[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
@@ -43,21 +47,38 @@ __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx
       q[2 * j + 1] += b * b;
     }
   }
+  float* mine = sm + (size_t)r0 * 2 * C;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    atomicAdd(&sm[v * 8 + j], s[j]);
-    atomicAdd(&sm[C + v * 8 + j], q[j]);
+    mine[v * 8 + j] = s[j];
+    mine[C + v * 8 + j] = q[j];
   }
   __syncthreads();
   const int cpg = C >> 5;
-  if (threadIdx.x < 32) {
-    double a = 0.0, b = 0.0;
+  if (threadIdx.x < 64) {
+    const int g = threadIdx.x & 31, which = threadIdx.x >> 5;  // which: 0 = sum, 1 = sum of squares
+    double a = 0.0;
     for (int j = 0; j < cpg; ++j) {
-      a += (double)sm[threadIdx.x * cpg + j];
-      b += (double)sm[C + threadIdx.x * cpg + j];
+      float c = 0.f;
+      for (int r = 0; r < rstep; ++r) c += sm[(size_t)r * 2 * C + which * C + g * cpg + j];
+      a += (double)c;
     }
-    atomicAdd(&sums[((int64_t)n * 32 + threadIdx.x) * 2], a);
-    atomicAdd(&sums[((int64_t)n * 32 + threadIdx.x) * 2 + 1], b);
+    partial[(((int64_t)n * chunks + blockIdx.x) * 32 + g) * 2 + which] = a;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int ticket = atomicAdd(&counters[n], 1);
+    is_last = (ticket == chunks - 1);
+    if (is_last) counters[n] = 0;  // self-reset for the next launch
+  }
+  __syncthreads();
+  if (is_last && threadIdx.x < 64) {
+    __threadfence();
+    const int g = threadIdx.x & 31, which = threadIdx.x >> 5;
+    double a = 0.0;
+    for (int c = 0; c < chunks; ++c) a += partial[(((int64_t)n * chunks + c) * 32 + g) * 2 + which];
+    sums[((int64_t)n * 32 + g) * 2 + which] = a;
   }
 }
 
@@ -213,8 +234,17 @@ static int gn_geometry(int C, int P, int* threads, int* rows_per_chunk, int* chu
 
 extern "C" {
 
-// sums must hold N*32*2 doubles; it is zeroed here (memsetAsync) before accumulation.
-int b200svd_gn_stats(const void* x, int64_t ldx, int64_t n, int64_t p, int c, void* sums, void* stream) {
+// sums: n*32*2 doubles (out).  scratch: at least b200svd_gn_scratch_doubles(n, p, c) doubles.  counters: n int32,
+// zero-initialised once by the caller (the kernel leaves them zero).
+int64_t b200svd_gn_scratch_doubles(int64_t n, int64_t p, int c) {
+  using namespace b200;
+  int threads, rpc, chunks;
+  if (gn_geometry(c, (int)p, &threads, &rpc, &chunks)) return -1;
+  return n * (int64_t)chunks * 64;
+}
+
+int b200svd_gn_stats(const void* x, int64_t ldx, int64_t n, int64_t p, int c, void* sums, void* scratch,
+                     void* counters, void* stream) {
   using namespace b200;
   int threads, rpc, chunks;
   if (gn_geometry(c, (int)p, &threads, &rpc, &chunks)) {
@@ -226,11 +256,18 @@ int b200svd_gn_stats(const void* x, int64_t ldx, int64_t n, int64_t p, int c, vo
     return 1;
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  cudaError_t e = cudaMemsetAsync(sums, 0, (size_t)n * 32 * 2 * sizeof(double), st);
-  if (e != cudaSuccess) return cuda_fail(e, "gn_stats memset");
   dim3 grid(chunks, (unsigned)n);
-  gn_stats_kernel<<<grid, threads, 2 * c * sizeof(float), st>>>(reinterpret_cast<const __nv_bfloat16*>(x), ldx, (int)p,
-                                                               c, rpc, reinterpret_cast<double*>(sums));
+  const int rstep = threads / (c / 8);
+  const size_t smem = (size_t)rstep * 2 * c * sizeof(float);
+  static size_t smem_set = 0;
+  if (smem > 48 * 1024 && smem > smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(gn_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_fail(e, "gn_stats smem attribute");
+    smem_set = smem;
+  }
+  gn_stats_kernel<<<grid, threads, smem, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), ldx, (int)p, c, rpc,
+                                             reinterpret_cast<double*>(sums), reinterpret_cast<double*>(scratch),
+                                             reinterpret_cast<int*>(counters));
   B200_CHECK_LAUNCH("gn_stats");
   return 0;
 }

@@ -229,6 +229,21 @@ def small_attn(q, k, v, *, b, s, heads, lq, lk, kv_per_pixel=True, out=None):
 # ----------------------------------------------------------------------------------------------------------------
 # norms
 # ----------------------------------------------------------------------------------------------------------------
+_GN_SCRATCH = {}
+
+
+def _gn_scratch(device, doubles, n):
+    """Per-device scratch for the deterministic GroupNorm reduction (chunk partials + self-resetting tickets).
+    Kernels on one stream run in order, so one buffer per device is enough."""
+    key = str(device)
+    cur = _GN_SCRATCH.get(key)
+    if cur is None or cur[0].numel() < doubles or cur[1].numel() < n:
+        cur = (torch.empty(max(doubles, 1 << 16), dtype=torch.float64, device=device),
+               torch.zeros(max(n, 1024), dtype=torch.int32, device=device))
+        _GN_SCRATCH[key] = cur
+    return cur
+
+
 def group_norm(x, n, p, gamma, beta, eps, *, silu=False, out=None, sums=None):
     """x: [(n p), C] bf16 rows; 32 groups; statistics over (p, C/32) per sample n.  Returns bf16 [(n p), C]."""
     assert x.dtype == torch.bfloat16 and x.dim() == 2 and x.stride(1) == 1 and x.shape[0] == n * p
@@ -237,7 +252,11 @@ def group_norm(x, n, p, gamma, beta, eps, *, silu=False, out=None, sums=None):
         sums = torch.empty((n, 32, 2), dtype=torch.float64, device=x.device)
     if out is None:
         out = torch.empty((n * p, Cc), dtype=torch.bfloat16, device=x.device)
-    _call("b200svd_gn_stats", _ptr(x), x.stride(0), n, p, Cc, _ptr(sums), _stream())
+    need = _lib.load().b200svd_gn_scratch_doubles(n, p, Cc)
+    if need < 0:
+        raise _lib.B200Error(f"group_norm: unsupported channel count {Cc}")
+    scratch, counters = _gn_scratch(x.device, need, n)
+    _call("b200svd_gn_stats", _ptr(x), x.stride(0), n, p, Cc, _ptr(sums), _ptr(scratch), _ptr(counters), _stream())
     _call("b200svd_gn_apply", _ptr(x), x.stride(0), _ptr(out), out.stride(0), n, p, Cc, _ptr(sums), _ptr(gamma),
           _ptr(beta), float(eps), 1 if silu else 0, _stream())
     return out
