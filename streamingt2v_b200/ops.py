@@ -15,11 +15,52 @@ from . import _lib
 from ._lib import ACT_GEGLU, ACT_GELU, ACT_NONE, ACT_SILU, GemmParams
 
 _launch_count = 0
+_PROFILE = None  # list of (family, flops, bytes, start_event, end_event) while profiling
 
 
 def launches() -> int:
     """Number of kernel launches issued through this module (bench.py's gpu_launches)."""
     return _launch_count
+
+
+class profile:
+    """Context manager: brackets every launch with CUDA events on the launching stream and returns per-family
+    (launches, total ms, algorithmic FLOPs, algorithmic bytes).  Used by bench.py for the live roofline numbers;
+    adds two event records per launch, so it is never active inside a timed region."""
+
+    def __enter__(self):
+        global _PROFILE
+        _PROFILE = []
+        return self
+
+    def __exit__(self, *exc):
+        global _PROFILE
+        recs, _PROFILE = _PROFILE, None
+        torch.cuda.synchronize()
+        self.families = {}
+        for fam, flops, nbytes, e0, e1 in recs:
+            f = self.families.setdefault(fam, dict(launches=0, ms=0.0, flops=0.0, bytes=0.0))
+            f["launches"] += 1
+            f["ms"] += e0.elapsed_time(e1)
+            f["flops"] += flops
+            f["bytes"] += nbytes
+        return False
+
+
+def _prof_begin():
+    if _PROFILE is None:
+        return None
+    e0 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    return e0
+
+
+def _prof_end(e0, family, flops=0.0, nbytes=0.0):
+    if e0 is None:
+        return
+    e1 = torch.cuda.Event(enable_timing=True)
+    e1.record()
+    _PROFILE.append((family, flops, nbytes, e0, e1))
 
 
 def _stream() -> C.c_void_p:
@@ -87,8 +128,15 @@ def gemm_raw(*, a, a_dims, a_strides, a_box, w, n, k, taps, tap_off, m_ext, m_bo
     p.s2 = float(s2)
     p.bn = int(bn)
     lib = _lib.load()
+    e0 = _prof_begin()
     _lib.check(lib.b200svd_gemm(C.byref(p), _stream()), "b200svd_gemm")
     _launch_count += 1
+    if e0 is not None:
+        rows = int(m_ext[0]) * int(m_ext[1]) * int(m_ext[2])
+        n_out = n // 2 if act == ACT_GEGLU else n
+        nbytes = 2.0 * rows * k + 2.0 * taps * n * k + (4.0 if out_fp32 else 2.0) * rows * n_out
+        nbytes += 2.0 * rows * n_out * ((res1 is not None) + (res2 is not None))
+        _prof_end(e0, "mtgemm", 2.0 * rows * k * n * taps, nbytes)
 
 
 def _epi_kwargs(rows, n_out, out, bias, fvec, rows_per_frame, act, s_acc, res1, s1, res2, s2, out_fp32):
@@ -196,11 +244,17 @@ def _conv_common(x, a_dims, a_strides, a_box, w, Cout, K, taps, m_ext, m_box, m_
 # ----------------------------------------------------------------------------------------------------------------
 # attention
 # ----------------------------------------------------------------------------------------------------------------
-def _call(name, *args):
+_FAMILY = {"b200svd_flash_attn": "flash_attn", "b200svd_small_attn": "small_attn", "b200svd_gn_stats": "groupnorm",
+           "b200svd_gn_apply": "groupnorm", "b200svd_layernorm": "layernorm"}
+
+
+def _call(name, *args, flops=0.0, nbytes=0.0):
     global _launch_count
     lib = _lib.load()
+    e0 = _prof_begin()
     _lib.check(getattr(lib, name)(*args), name)
     _launch_count += 1
+    _prof_end(e0, _FAMILY.get(name, "glue"), flops, nbytes)
 
 
 def flash_attn(qkv, n, s, heads, out=None):
@@ -210,7 +264,8 @@ def flash_attn(qkv, n, s, heads, out=None):
     assert qkv.shape == (n * s, 3 * Cc)
     if out is None:
         out = torch.empty((n * s, Cc), dtype=torch.bfloat16, device=qkv.device)
-    _call("b200svd_flash_attn", _ptr(qkv), qkv.stride(0), _ptr(out), out.stride(0), n, s, heads, 64 ** -0.5, _stream())
+    _call("b200svd_flash_attn", _ptr(qkv), qkv.stride(0), _ptr(out), out.stride(0), n, s, heads, 64 ** -0.5, _stream(),
+          flops=4.0 * n * heads * float(s) * s * 64, nbytes=2.0 * n * s * 4 * Cc)
     return out
 
 
@@ -222,7 +277,9 @@ def small_attn(q, k, v, *, b, s, heads, lq, lk, kv_per_pixel=True, out=None):
     if out is None:
         out = torch.empty((b * lq * s, Cc), dtype=torch.bfloat16, device=q.device)
     _call("b200svd_small_attn", _ptr(q), q.stride(0), _ptr(k), k.stride(0), _ptr(v), v.stride(0), _ptr(out),
-          out.stride(0), b, s, heads, lq, lk, 1 if kv_per_pixel else 0, 64 ** -0.5, _stream())
+          out.stride(0), b, s, heads, lq, lk, 1 if kv_per_pixel else 0, 64 ** -0.5, _stream(),
+          flops=4.0 * b * s * heads * lq * lk * 64,
+          nbytes=2.0 * Cc * (2 * b * lq * s + 2 * b * lk * (s if kv_per_pixel else 1)))
     return out
 
 
@@ -256,9 +313,10 @@ def group_norm(x, n, p, gamma, beta, eps, *, silu=False, out=None, sums=None):
     if need < 0:
         raise _lib.B200Error(f"group_norm: unsupported channel count {Cc}")
     scratch, counters = _gn_scratch(x.device, need, n)
-    _call("b200svd_gn_stats", _ptr(x), x.stride(0), n, p, Cc, _ptr(sums), _ptr(scratch), _ptr(counters), _stream())
+    _call("b200svd_gn_stats", _ptr(x), x.stride(0), n, p, Cc, _ptr(sums), _ptr(scratch), _ptr(counters), _stream(),
+          nbytes=2.0 * n * p * Cc)
     _call("b200svd_gn_apply", _ptr(x), x.stride(0), _ptr(out), out.stride(0), n, p, Cc, _ptr(sums), _ptr(gamma),
-          _ptr(beta), float(eps), 1 if silu else 0, _stream())
+          _ptr(beta), float(eps), 1 if silu else 0, _stream(), nbytes=4.0 * n * p * Cc)
     return out
 
 
@@ -269,7 +327,8 @@ def layer_norm(x, gamma, beta, eps=1e-5, *, fvec=None, rows_per_frame=1, xsum=No
         out = torch.empty((rows, Cc), dtype=torch.bfloat16, device=x.device)
     _call("b200svd_layernorm", _ptr(x), x.stride(0), _ptr(out), out.stride(0), rows, Cc, _ptr(gamma), _ptr(beta),
           float(eps), _ptr(fvec), fvec.stride(0) if fvec is not None else 0, rows_per_frame, _ptr(xsum),
-          xsum.stride(0) if xsum is not None else 0, 1 if silu else 0, _stream())
+          xsum.stride(0) if xsum is not None else 0, 1 if silu else 0, _stream(),
+          nbytes=2.0 * rows * Cc * (2 + (xsum is not None)))
     return out
 
 

@@ -1,0 +1,66 @@
+"""CPU: host logic of the executor (weight packing, epilogue composition, concat/skip plumbing, conditioning
+hoist) checked against the oracle with tests/fake_ops.py standing in for the CUDA ops (same signatures, torch-CPU
+arithmetic with bf16 rounding where the kernels round).  No product code path uses fake_ops."""
+import dataclasses
+
+import pytest
+import torch
+
+import fake_ops
+
+
+def _rel(a, b):
+    return ((a - b).norm() / b.norm()).item()
+
+
+@pytest.fixture()
+def patched_model(monkeypatch):
+    from streamingt2v_b200 import model
+    monkeypatch.setattr(model, "ops", fake_ops)
+    return model
+
+
+@pytest.mark.parametrize("apm,T,h,w", [(False, 8, 8, 8), (True, 7, 8, 16)])
+def test_executor_wiring(patched_model, apm, T, h, w):
+    from oracle import streaming_svd_oracle as orc
+    from streamingt2v_b200 import arch, synth
+    cfg = dataclasses.replace(arch.TINY, use_apm=apm)
+    sd_u = arch.synth_state_dict_fast(arch.unet_param_shapes(cfg), 21)
+    sd_c = arch.synth_state_dict_fast(arch.controlnet_param_shapes(cfg), 22)
+    x, t, c, kw = synth.make_inputs(cfg, T=T, h=h, w=w, seed=9, ctx_tokens=17 if apm else 1)
+    with torch.no_grad():
+        ref = orc.streaming_wrapper_forward(sd_u, sd_c, cfg, x, t, c, **kw)
+    eng = patched_model.B200Denoiser(cfg, sd_u, sd_c, "cpu")
+    out = eng.forward(x, t, c, batch_size=kw["batch_size"], num_video_frames=T, ctrl_frames=kw["ctrl_frames"])
+    assert out.shape == ref.shape and out.dtype == torch.float32
+    r = _rel(out, ref)
+    assert r < 3e-2, r
+    # conditioning cache: same tensors -> hit; in-place change -> miss and a different answer
+    key = eng._cond_key
+    out2 = eng.forward(x, t, c, batch_size=kw["batch_size"], num_video_frames=T, ctrl_frames=kw["ctrl_frames"])
+    assert eng._cond_key == key and torch.equal(out, out2)
+    c["crossattn"].mul_(0.5)
+    out3 = eng.forward(x, t, c, batch_size=kw["batch_size"], num_video_frames=T, ctrl_frames=kw["ctrl_frames"])
+    assert eng._cond_key != key and not torch.equal(out, out3)
+
+
+def test_no_controlnet_branch(patched_model):
+    from oracle import streaming_svd_oracle as orc
+    from streamingt2v_b200 import arch, synth
+    cfg = arch.TINY
+    sd_u = arch.synth_state_dict_fast(arch.unet_param_shapes(cfg), 31)
+    x, t, c, kw = synth.make_inputs(cfg, T=8, h=8, w=8, seed=3)
+    eng = patched_model.B200Denoiser(cfg, sd_u, None, "cpu")
+    out = eng.forward(x, t, c, batch_size=2, num_video_frames=8)
+    with torch.no_grad():
+        ref = orc.unet_forward(sd_u, cfg, torch.cat([x, c["concat"]], 1), t, c["crossattn"], c["vector"], 8, 7)
+    assert _rel(out, ref) < 3e-2
+
+
+def test_wrapper_refuses_cpu():
+    from streamingt2v_b200 import arch
+    from streamingt2v_b200.wrapper import B200StreamingWrapper
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        B200StreamingWrapper(arch.TINY, {}, None)
