@@ -267,6 +267,10 @@ def run_ours(args):
             step(cur, td, cd, ctrl_d, 1)
         fam = {k: dict(launches=v["launches"], ms=round(v["ms"], 3), tflops=round(v["flops"] / 1e12, 3),
                        gbytes=round(v["bytes"] / 1e9, 3)) for k, v in prof.families.items()}
+        if os.environ.get("B200SVD_BENCH_SHAPES"):
+            with open(os.environ["B200SVD_BENCH_SHAPES"], "w") as fh:
+                for d_, n_, ms_, tf_ in ops.summarize_records(prof.launch_records, "mtgemm", 60):
+                    fh.write(f"{ms_:9.3f} ms n={n_:3d} avg={ms_ / n_:7.3f} {tf_:7.1f} TF/s  {d_}\n")
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))

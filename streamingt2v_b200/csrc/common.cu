@@ -89,6 +89,11 @@ int encode_tmap_bf16_noswz(CUtensorMap* out, const void* gptr, int rank, const u
   return encode_impl(out, gptr, rank, dims, strides_bytes, box, CU_TENSOR_MAP_SWIZZLE_NONE);
 }
 
+int encode_tmap_bf16_sw64(CUtensorMap* out, const void* gptr, int rank, const uint64_t* dims,
+                          const uint64_t* strides_bytes, const uint32_t* box) {
+  return encode_impl(out, gptr, rank, dims, strides_bytes, box, CU_TENSOR_MAP_SWIZZLE_64B);
+}
+
 int sm_count() {
   static int n = 0;
   if (n == 0) {

@@ -1,5 +1,6 @@
-// Multi-tap tensor-core GEMM for sm_100a: TMA (rank-5 activation view) -> smem (128B swizzle) -> tcgen05.mma
-// (fp32 accumulators in TMEM) -> fused epilogue.  See include/b200svd.h for the contract.
+// Multi-tap tensor-core GEMM for sm_100a (v3).
+// TMA (rank-5 activation view) -> smem (128B swizzle) -> tcgen05.mma (fp32 accumulators in TMEM, double buffered)
+// -> fused epilogue -> swizzled smem staging -> TMA store.  See include/b200svd.h for the contract.
 //
 // Replaces, underneath StreamingWrapper.forward (reference code/models/diffusion/wrappers.py:23-78):
 //   nn.Linear            code/models/svd/sgm/modules/attention.py:94-120,262-351, video_attention.py:23-168
@@ -8,10 +9,17 @@
 //   + their elementwise neighbours (bias, emb add openaimodel.py:346-352, GEGLU attention.py:94-101,
 //     residual / AlphaBlender diffusionmodules/util.py:358-370).
 //
-// CTA = 128 output rows x BN output columns; 6 warps: warp0 = TMA producer, warp1 = MMA issuer + TMEM owner,
-// warps 2..5 = epilogue (one TMEM lane quadrant each).  K loop = taps x ceil(K/64) stages through a
-// STAGES-deep mbarrier ring.  Two CTAs co-reside per SM (smem/TMEM sized for it) so one CTA's epilogue overlaps
-// the other's main loop.
+// One persistent CTA per SM walks a contiguous run of 128 x BN output tiles (N tile fastest).  20 warps:
+//   warp 0       TMA producer for A/B (stage ring runs ahead across tiles)
+//   warp 1       MMA issuer + TMEM owner (two accumulator buffers: tile i's epilogue overlaps tile i+1's main loop)
+//   warp 2       TMA producer for the residual operand (ring of 3 sub-tile buffers, runs ahead of the epilogue)
+//   warps 4..19  epilogue: 4 per TMEM lane quadrant, 16 columns each per 64-column sub-tile; results are written
+//                thread-per-row into 128B/64B-swizzled staging (bank-conflict free) and leave through one TMA store
+//                per quadrant and sub-tile (hardware clips ragged edges) — no per-element address arithmetic.
+// Why: ncu on v2 (profiles/r01_ncu_gemm_*) showed the small-K layers bound by epilogue instruction issue
+// (runtime division + 64-bit addressing in copy loops, IEEE divide / erff in activations) and shared-memory bank
+// conflicts, and the large-K layers by shared-memory bandwidth per FLOP; v3 removes the former and offers a
+// 256-wide tile for the latter.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <string.h>
@@ -25,16 +33,18 @@ namespace b200 {
 struct GemmDev {
   int32_t tap_off[B200SVD_MAX_TAPS][5];
   uint32_t taps, kblocks;
-  uint32_t n;            // GEMM N (weight rows)
+  uint32_t n;  // GEMM N (weight rows)
   uint32_t n_tiles;
+  uint32_t total_tiles, tiles_per_cta;
   uint32_t m_ext[3];
-  uint32_t m_lb[3];      // log2 of box
+  uint32_t m_lb[3];  // log2 of box
   uint32_t m_tiles[3];
   uint32_t m_adim[3];
   int64_t out_rs[3];
   void* out;
   int64_t ldo;
   int32_t out_fp32;
+  int32_t tma_epi;  // 1: staged TMA-store epilogue (bf16 out), 0: direct per-row stores (fp32 out)
   const float* bias;
   const float* fvec;
   int64_t ldf;
@@ -52,50 +62,89 @@ struct GemmDev {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
+constexpr int EPI_WARPS = 16;
+constexpr int FIRST_EPI_WARP = 4;
+constexpr int NUM_THREADS = (FIRST_EPI_WARP + EPI_WARPS) * 32;  // 640
+constexpr int RES_BUFS = 3;
+constexpr int RES_BUF_BYTES = 128 * 64 * 2;  // one 128-row x 64-column bf16 sub-tile
+constexpr int OUT_BUF_BYTES = 32 * 64 * 2;   // one quadrant (32 rows) x 64 columns
 
 template <int BN>
 struct TileCfg {
   static constexpr int B_STAGE_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STAGES = (BN >= 128) ? 3 : 4;
-  static constexpr int TMEM_COLS = (BN <= 32) ? 32 : (BN <= 64) ? 64 : (BN <= 128) ? 128 : 256;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int STAGES = (BN >= 256) ? 3 : (BN >= 128) ? 4 : 6;
+  static constexpr int ACC_STRIDE = (BN <= 32) ? 32 : (BN <= 64) ? 64 : (BN <= 128) ? 128 : 256;
+  static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
+  static constexpr int NSUB = (BN + 63) / 64;
+  static constexpr int OUT_BYTES = 4 * 2 * OUT_BUF_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + RES_BUFS * RES_BUF_BYTES + OUT_BYTES + 512;
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+  static_assert(STAGE_BYTES % 1024 == 0, "stage alignment");
 };
 
-template <int BN>
-__global__ void __launch_bounds__(192, 2)
-mtgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmDev p) {
-  using Cfg = TileCfg<BN>;
-  constexpr int STAGES = Cfg::STAGES;
-  extern __shared__ uint8_t smem_raw[];
-  // 1024-byte alignment required by SWIZZLE_128B operands
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* accum_bar = empty_bar + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-
-  // tile coordinates: n tile fastest so that CTAs sharing an A tile run back to back (A is re-read from L2)
-  const uint32_t n_tile = blockIdx.x % p.n_tiles;
-  uint32_t mt = blockIdx.x / p.n_tiles;
+__device__ __forceinline__ void decode_tile(const GemmDev& p, uint32_t tile, uint32_t& n_tile, uint32_t& mb1,
+                                            uint32_t& mb2, uint32_t& mb3) {
+  n_tile = tile % p.n_tiles;
+  uint32_t mt = tile / p.n_tiles;
   const uint32_t t1 = mt % p.m_tiles[0];
   mt /= p.m_tiles[0];
   const uint32_t t2 = mt % p.m_tiles[1];
   const uint32_t t3 = mt / p.m_tiles[1];
-  const uint32_t mb1 = t1 << p.m_lb[0], mb2 = t2 << p.m_lb[1], mb3 = t3 << p.m_lb[2];
-  const uint32_t n0 = n_tile * BN;
+  mb1 = t1 << p.m_lb[0];
+  mb2 = t2 << p.m_lb[1];
+  mb3 = t3 << p.m_lb[2];
+}
+
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+mtgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+              const __grid_constant__ CUtensorMap tmO64, const __grid_constant__ CUtensorMap tmO32,
+              const __grid_constant__ CUtensorMap tmR64, const __grid_constant__ CUtensorMap tmR32, const GemmDev p) {
+  using Cfg = TileCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ __align__(1024) uint8_t smem[];  // SWIZZLE_128B operands need 1024-byte alignment
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  uint8_t* res_base = smem + STAGES * Cfg::STAGE_BYTES;
+  uint8_t* out_base = res_base + RES_BUFS * RES_BUF_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(out_base + Cfg::OUT_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* acc_full = empty_bar + STAGES;    // [2]
+  uint64_t* acc_empty = acc_full + 2;         // [2]
+  uint64_t* res_full = acc_empty + 2;         // [RES_BUFS]
+  uint64_t* res_empty = res_full + RES_BUFS;  // [RES_BUFS]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_empty + RES_BUFS);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const uint32_t tile_begin = blockIdx.x * p.tiles_per_cta;
+  const uint32_t tile_end = min(tile_begin + p.tiles_per_cta, p.total_tiles);
+  const bool geglu = (p.act == B200SVD_ACT_GEGLU);
+  const uint32_t n_out = geglu ? p.n / 2 : p.n;
+  const uint32_t tile_out_w = geglu ? (uint32_t)BN / 2 : (uint32_t)BN;  // output columns per tile
+  const uint32_t nsub_out = (tile_out_w + 63) / 64;
+  const bool use_res_ring = p.tma_epi && p.res1 != nullptr;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
+    if (p.tma_epi) {
+      prefetch_tmap(&tmO64);
+      prefetch_tmap(&tmO32);
+    }
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(accum_bar, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], EPI_WARPS);  // one arrive per epilogue warp
+    }
+    for (int b = 0; b < RES_BUFS; ++b) {
+      mbar_init(&res_full[b], 1);
+      mbar_init(&res_empty[b], EPI_WARPS);
+    }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -106,32 +155,35 @@ mtgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-
-  const uint32_t total_iters = p.taps * p.kblocks;
+  const uint32_t iters_per_tile = p.taps * p.kblocks;
 
   if (warp == 0) {
     if (lane == 0) {
-      // ===================== TMA producer =====================
-      int base[5] = {0, 0, 0, 0, 0};
-      base[p.m_adim[0]] += (int)mb1;
-      base[p.m_adim[1]] += (int)mb2;
-      base[p.m_adim[2]] += (int)mb3;
+      // ===================== TMA producer (A, B) =====================
       uint32_t it = 0;
-      for (uint32_t tap = 0; tap < p.taps; ++tap) {
-        const int c0 = p.tap_off[tap][0];
-        const int c1 = base[1] + p.tap_off[tap][1];
-        const int c2 = base[2] + p.tap_off[tap][2];
-        const int c3 = base[3] + p.tap_off[tap][3];
-        const int c4 = base[4] + p.tap_off[tap][4];
-        for (uint32_t kb = 0; kb < p.kblocks; ++kb, ++it) {
-          const uint32_t s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1;
-          mbar_wait(&empty_bar[s], ph ^ 1);
-          uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
-          uint8_t* sb = sa + A_STAGE_BYTES;
-          mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
-          tma_load_5d(sa, &tmA, &full_bar[s], c0 + (int)(kb * BK), c1, c2, c3, c4);
-          tma_load_3d(sb, &tmB, &full_bar[s], (int)(kb * BK), (int)n0, (int)tap);
+      for (uint32_t tile = tile_begin; tile < tile_end; ++tile) {
+        uint32_t n_tile, mb1, mb2, mb3;
+        decode_tile(p, tile, n_tile, mb1, mb2, mb3);
+        int base[5] = {0, 0, 0, 0, 0};
+        base[p.m_adim[0]] += (int)mb1;
+        base[p.m_adim[1]] += (int)mb2;
+        base[p.m_adim[2]] += (int)mb3;
+        const int n0 = (int)(n_tile * BN);
+        for (uint32_t tap = 0; tap < p.taps; ++tap) {
+          const int c0 = p.tap_off[tap][0];
+          const int c1 = base[1] + p.tap_off[tap][1];
+          const int c2 = base[2] + p.tap_off[tap][2];
+          const int c3 = base[3] + p.tap_off[tap][3];
+          const int c4 = base[4] + p.tap_off[tap][4];
+          for (uint32_t kb = 0; kb < p.kblocks; ++kb, ++it) {
+            const uint32_t s = it % STAGES;
+            const uint32_t ph = (it / STAGES) & 1;
+            mbar_wait(&empty_bar[s], ph ^ 1);
+            uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
+            mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+            tma_load_5d(sa, &tmA, &full_bar[s], c0 + (int)(kb * BK), c1, c2, c3, c4);
+            tma_load_3d(sa + A_STAGE_BYTES, &tmB, &full_bar[s], (int)(kb * BK), n0, (int)tap);
+          }
         }
       }
     }
@@ -139,150 +191,287 @@ mtgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     if (lane == 0) {
       // ===================== MMA issuer =====================
       constexpr uint32_t idesc = make_idesc_f16(BM, BN, /*bf16*/ 1, 0, 0);
-      for (uint32_t it = 0; it < total_iters; ++it) {
-        const uint32_t s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        mbar_wait(&full_bar[s], ph);
+      uint32_t it = 0, tcount = 0;
+      for (uint32_t tile = tile_begin; tile < tile_end; ++tile, ++tcount) {
+        const uint32_t b = tcount & 1;
+        mbar_wait(&acc_empty[b], ((tcount >> 1) & 1) ^ 1);  // epilogue has drained this accumulator buffer
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + s * Cfg::STAGE_BYTES);
-        const uint64_t adesc = smem_desc_k_sw128(sa);
-        const uint64_t bdesc = smem_desc_k_sw128(sa + A_STAGE_BYTES);
+        const uint32_t tacc = tmem_base + b * Cfg::ACC_STRIDE;
+        for (uint32_t i = 0; i < iters_per_tile; ++i, ++it) {
+          const uint32_t s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * Cfg::STAGE_BYTES);
+          const uint64_t adesc = smem_desc_k_sw128(sa);
+          const uint64_t bdesc = smem_desc_k_sw128(sa + A_STAGE_BYTES);
 #pragma unroll
-        for (int kk = 0; kk < BK / 16; ++kk) {
-          // advance 16 elements (32 B) along K inside the 128B swizzle atom: +2 in the (addr>>4) field
-          umma_f16_ss(tmem_base, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc,
-                      (it > 0 || kk > 0) ? 1u : 0u);
+          for (int kk = 0; kk < BK / 16; ++kk) {
+            // advance 16 elements (32 B) along K inside the 128B swizzle atom: +2 in the (addr>>4) field
+            umma_f16_ss(tacc, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, (i > 0 || kk > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs have read it
         }
-        umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs have read it
+        umma_commit(&acc_full[b]);  // accumulator complete
       }
-      umma_commit(accum_bar);  // accumulator complete
     }
     __syncwarp();
-  } else {
-    // ===================== epilogue warps (2..5) =====================
-    const int q = warp & 3;  // TMEM lane quadrant this warp may access
-    const int r = q * 32 + lane;
-    const uint32_t lb1 = p.m_lb[0], lb2 = p.m_lb[1];
-    const uint32_t m1 = mb1 + (r & ((1u << lb1) - 1));
-    const uint32_t m2 = mb2 + ((r >> lb1) & ((1u << lb2) - 1));
-    const uint32_t m3 = mb3 + (r >> (lb1 + lb2));
-    const bool valid = (m1 < p.m_ext[0]) && (m2 < p.m_ext[1]) && (m3 < p.m_ext[2]);
-    const int64_t row = (int64_t)m1 * p.out_rs[0] + (int64_t)m2 * p.out_rs[1] + (int64_t)m3 * p.out_rs[2];
-    const float* fv = nullptr;
-    if (p.fvec != nullptr && valid) fv = p.fvec + (row / p.rows_per_frame) * p.ldf;
-
-    mbar_wait(accum_bar, 0);
-    tc_fence_after();
-    const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
-    const bool geglu = (p.act == B200SVD_ACT_GEGLU);
-    const int ncols = geglu ? BN / 2 : BN;
-    const uint32_t n_out = geglu ? p.n / 2 : p.n;
-    const uint32_t ocol0 = geglu ? n_tile * (BN / 2) : n0;
-
-    for (int c0 = 0; c0 < ncols; c0 += 16) {
-      if (ocol0 + c0 >= n_out) break;  // warp-uniform
-      uint32_t va[16];
-      uint32_t vg[16];
-      tmem_ld16(tlane + (uint32_t)c0, va);
-      if (geglu) tmem_ld16(tlane + (uint32_t)(BN / 2 + c0), vg);
-      tmem_ld_wait();
-      if (!valid) continue;
-      float v[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(va[j]);
-      const uint32_t wcol = n0 + c0;  // weight-row index of the (first) accumulator column
-      const uint32_t ocol = ocol0 + c0;
-      const bool full = (ocol + 16 <= n_out);
-      if (p.bias != nullptr) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (full || ocol + j < n_out) v[j] += __ldg(p.bias + wcol + j);
-      }
-      if (fv != nullptr) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (full || ocol + j < n_out) v[j] += __ldg(fv + ocol + j);
-      }
-      if (p.act == B200SVD_ACT_SILU) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = silu_f(v[j]);
-      } else if (p.act == B200SVD_ACT_GELU) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = gelu_f(v[j]);
-      } else if (geglu) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float g = __uint_as_float(vg[j]);
-          if (p.bias != nullptr) g += __ldg(p.bias + wcol + BN / 2 + j);
-          v[j] = v[j] * gelu_f(g);
-        }
-      }
-      if (p.s_acc != 1.0f) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] *= p.s_acc;
-      }
-      if (p.res1 != nullptr) {
-        const __nv_bfloat16* rp = p.res1 + row * p.ld1 + ocol;
-        if (full) {
-          const uint4 a = __ldg(reinterpret_cast<const uint4*>(rp));
-          const uint4 b = __ldg(reinterpret_cast<const uint4*>(rp) + 1);
-          const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            v[2 * j] += p.s1 * bf16_lo(w[j]);
-            v[2 * j + 1] += p.s1 * bf16_hi(w[j]);
-          }
-        } else {
-          for (int j = 0; j < 16; ++j)
-            if (ocol + j < n_out) v[j] += p.s1 * __bfloat162float(rp[j]);
-        }
-      }
-      if (p.res2 != nullptr) {
-        const __nv_bfloat16* rp = p.res2 + row * p.ld2 + ocol;
-        if (full) {
-          const uint4 a = __ldg(reinterpret_cast<const uint4*>(rp));
-          const uint4 b = __ldg(reinterpret_cast<const uint4*>(rp) + 1);
-          const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            v[2 * j] += p.s2 * bf16_lo(w[j]);
-            v[2 * j + 1] += p.s2 * bf16_hi(w[j]);
-          }
-        } else {
-          for (int j = 0; j < 16; ++j)
-            if (ocol + j < n_out) v[j] += p.s2 * __bfloat162float(rp[j]);
-        }
-      }
-      if (p.out_fp32) {
-        float* op = reinterpret_cast<float*>(p.out) + row * p.ldo + ocol;
-        if (full) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            reinterpret_cast<float4*>(op)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        } else {
-          for (int j = 0; j < 16; ++j)
-            if (ocol + j < n_out) op[j] = v[j];
-        }
-      } else {
-        __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldo + ocol;
-        if (full) {
-          uint4 o0, o1;
-          o0.x = pack_bf16x2(v[0], v[1]);
-          o0.y = pack_bf16x2(v[2], v[3]);
-          o0.z = pack_bf16x2(v[4], v[5]);
-          o0.w = pack_bf16x2(v[6], v[7]);
-          o1.x = pack_bf16x2(v[8], v[9]);
-          o1.y = pack_bf16x2(v[10], v[11]);
-          o1.z = pack_bf16x2(v[12], v[13]);
-          o1.w = pack_bf16x2(v[14], v[15]);
-          reinterpret_cast<uint4*>(op)[0] = o0;
-          reinterpret_cast<uint4*>(op)[1] = o1;
-        } else {
-          for (int j = 0; j < 16; ++j)
-            if (ocol + j < n_out) op[j] = __float2bfloat16(v[j]);
+  } else if (warp == 2) {
+    if (lane == 0 && use_res_ring) {
+      // ===================== TMA producer (residual sub-tiles) =====================
+      uint32_t rcount = 0;
+      for (uint32_t tile = tile_begin; tile < tile_end; ++tile) {
+        uint32_t n_tile, mb1, mb2, mb3;
+        decode_tile(p, tile, n_tile, mb1, mb2, mb3);
+        const uint32_t otile0 = n_tile * tile_out_w;
+        for (uint32_t s = 0; s < nsub_out; ++s) {
+          const uint32_t ocol0 = otile0 + 64 * s;
+          if (ocol0 >= n_out) break;
+          const uint32_t rem = tile_out_w - 64 * s;
+          const uint32_t subw = rem >= 64 ? 64u : rem;
+          const uint32_t rb = rcount % RES_BUFS;
+          mbar_wait(&res_empty[rb], ((rcount / RES_BUFS) & 1) ^ 1);
+          mbar_expect_tx(&res_full[rb], subw * 2 * 128);
+          tma_load_5d(res_base + rb * RES_BUF_BYTES, subw == 64 ? &tmR64 : &tmR32, &res_full[rb], (int)ocol0, (int)mb1,
+                      (int)mb2, (int)mb3, 0);
+          ++rcount;
         }
       }
     }
+  } else if (warp >= FIRST_EPI_WARP) {
+    // ===================== epilogue warps (4..19) =====================
+    const int e = warp - FIRST_EPI_WARP;
+    const int q = e & 3;   // TMEM lane quadrant (== warp % 4)
+    const int g = e >> 2;  // 16-column group inside every 64-column sub-tile
+    const int r = q * 32 + lane;
+    const uint32_t lb1 = p.m_lb[0], lb2 = p.m_lb[1];
+    const uint32_t qoff = (uint32_t)(q * 32);
+    const uint32_t qo1 = qoff & ((1u << lb1) - 1);
+    const uint32_t qo2 = (qoff >> lb1) & ((1u << lb2) - 1);
+    const uint32_t qo3 = qoff >> (lb1 + lb2);
+    uint8_t* outq = out_base + q * 2 * OUT_BUF_BYTES;
+    const bool bias_vec = p.bias != nullptr && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0;
+    const bool fvec_vec = p.fvec != nullptr && (reinterpret_cast<uintptr_t>(p.fvec) & 15) == 0 && (p.ldf & 3) == 0;
+
+    uint32_t tcount = 0, ocount = 0, rcount = 0;
+    for (uint32_t tile = tile_begin; tile < tile_end; ++tile, ++tcount) {
+      uint32_t n_tile, mb1, mb2, mb3;
+      decode_tile(p, tile, n_tile, mb1, mb2, mb3);
+      const uint32_t n0 = n_tile * BN;
+      const uint32_t otile0 = n_tile * tile_out_w;
+      const uint32_t m1 = mb1 + (r & ((1u << lb1) - 1));
+      const uint32_t m2 = mb2 + ((r >> lb1) & ((1u << lb2) - 1));
+      const uint32_t m3 = mb3 + (r >> (lb1 + lb2));
+      const bool valid = (m1 < p.m_ext[0]) && (m2 < p.m_ext[1]) && (m3 < p.m_ext[2]);
+      const int64_t row = (int64_t)m1 * p.out_rs[0] + (int64_t)m2 * p.out_rs[1] + (int64_t)m3 * p.out_rs[2];
+      const float* fv = nullptr;
+      if (p.fvec != nullptr && valid) fv = p.fvec + (row / p.rows_per_frame) * p.ldf;
+
+      const uint32_t b = tcount & 1;
+      mbar_wait(&acc_full[b], (tcount >> 1) & 1);
+      tc_fence_after();
+      const uint32_t tlane = tmem_base + b * Cfg::ACC_STRIDE + ((uint32_t)(q * 32) << 16);
+
+      // per-16-column math shared by both epilogue flavours; v = accumulators on entry, finished values on exit
+      auto finish16 = [&](float (&v)[16], const uint32_t (&vg)[16], uint32_t wcol, uint32_t ocol, bool full) {
+        if (p.bias != nullptr) {
+          if (full && bias_vec) {
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + wcol) + j4);
+              v[4 * j4] += bb.x; v[4 * j4 + 1] += bb.y; v[4 * j4 + 2] += bb.z; v[4 * j4 + 3] += bb.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (full || ocol + j < n_out) v[j] += __ldg(p.bias + wcol + j);
+          }
+        }
+        if (fv != nullptr) {
+          if (full && fvec_vec) {
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const float4 bb = __ldg(reinterpret_cast<const float4*>(fv + ocol) + j4);
+              v[4 * j4] += bb.x; v[4 * j4 + 1] += bb.y; v[4 * j4 + 2] += bb.z; v[4 * j4 + 3] += bb.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (full || ocol + j < n_out) v[j] += __ldg(fv + ocol + j);
+          }
+        }
+        if (p.act == B200SVD_ACT_SILU) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = silu_fast(v[j]);
+        } else if (p.act == B200SVD_ACT_GELU) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = gelu_fast(v[j]);
+        } else if (geglu) {
+          float gt[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) gt[j] = __uint_as_float(vg[j]);
+          if (p.bias != nullptr) {
+            if (full && bias_vec) {
+#pragma unroll
+              for (int j4 = 0; j4 < 4; ++j4) {
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + wcol + BN / 2) + j4);
+                gt[4 * j4] += bb.x; gt[4 * j4 + 1] += bb.y; gt[4 * j4 + 2] += bb.z; gt[4 * j4 + 3] += bb.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (full || ocol + j < n_out) gt[j] += __ldg(p.bias + wcol + BN / 2 + j);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = v[j] * gelu_fast(gt[j]);
+        }
+        if (p.s_acc != 1.0f) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] *= p.s_acc;
+        }
+      };
+
+      if (p.tma_epi) {
+        for (uint32_t s = 0; s < nsub_out; ++s) {
+          const uint32_t ocol0 = otile0 + 64 * s;
+          if (ocol0 >= n_out) break;  // CTA-uniform (same rule in the residual producer)
+          const uint32_t rem = tile_out_w - 64 * s;
+          const uint32_t subw = rem >= 64 ? 64u : rem;  // 64 or 32
+          const bool last_sub = (s + 1 == nsub_out) || (otile0 + 64 * (s + 1) >= n_out);
+          uint32_t rb = 0;
+          if (use_res_ring) {
+            rb = rcount % RES_BUFS;
+            mbar_wait(&res_full[rb], (rcount / RES_BUFS) & 1);
+          }
+          uint8_t* ob = outq + (ocount & 1) * OUT_BUF_BYTES;
+          if ((uint32_t)(16 * g) < subw) {
+            const uint32_t acol = 64 * s + 16 * g;  // accumulator column (value half for GEGLU)
+            uint32_t va[16], vg[16];
+            tmem_ld16(tlane + acol, va);
+            if (geglu) tmem_ld16(tlane + (uint32_t)(BN / 2) + acol, vg);
+            tmem_ld_wait();
+            float v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(va[j]);
+            const uint32_t ocol = ocol0 + 16 * g;
+            const bool full = (ocol + 16) <= n_out;
+            finish16(v, vg, n0 + acol, ocol, full);
+            // swizzled 16-byte chunk positions of this thread's two chunks (c = 2g, 2g+1)
+            const uint32_t c_lo = 2 * g, c_hi = 2 * g + 1;
+            if (use_res_ring) {
+              const uint8_t* rrow;
+              uint32_t x;
+              if (subw == 64) {
+                rrow = res_base + rb * RES_BUF_BYTES + r * 128;
+                x = (uint32_t)(r & 7);
+              } else {
+                rrow = res_base + rb * RES_BUF_BYTES + r * 64;
+                x = (uint32_t)((r >> 1) & 3);
+              }
+              const uint4 a = *reinterpret_cast<const uint4*>(rrow + ((c_lo ^ x) << 4));
+              const uint4 bq = *reinterpret_cast<const uint4*>(rrow + ((c_hi ^ x) << 4));
+              const uint32_t w[8] = {a.x, a.y, a.z, a.w, bq.x, bq.y, bq.z, bq.w};
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                v[2 * j] += p.s1 * bf16_lo(w[j]);
+                v[2 * j + 1] += p.s1 * bf16_hi(w[j]);
+              }
+            }
+            if (p.res2 != nullptr && valid) {
+              // second residual (only the temporal AlphaBlender GEMMs): read straight from global, own row
+              const __nv_bfloat16* rp = p.res2 + row * p.ld2 + ocol;
+              if (full) {
+                const uint4 a = __ldg(reinterpret_cast<const uint4*>(rp));
+                const uint4 bq = __ldg(reinterpret_cast<const uint4*>(rp) + 1);
+                const uint32_t w[8] = {a.x, a.y, a.z, a.w, bq.x, bq.y, bq.z, bq.w};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  v[2 * j] += p.s2 * bf16_lo(w[j]);
+                  v[2 * j + 1] += p.s2 * bf16_hi(w[j]);
+                }
+              } else {
+                for (int j = 0; j < 16; ++j)
+                  if (ocol + j < n_out) v[j] += p.s2 * __bfloat162float(rp[j]);
+              }
+            }
+            uint8_t* orow;
+            uint32_t xo;
+            if (subw == 64) {
+              orow = ob + lane * 128;
+              xo = (uint32_t)(lane & 7);
+            } else {
+              orow = ob + lane * 64;
+              xo = (uint32_t)((lane >> 1) & 3);
+            }
+            *reinterpret_cast<uint4*>(orow + ((c_lo ^ xo) << 4)) =
+                make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+            *reinterpret_cast<uint4*>(orow + ((c_hi ^ xo) << 4)) =
+                make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]),
+                           pack_bf16x2(v[14], v[15]));
+            fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA store
+          }
+          if (use_res_ring) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&res_empty[rb]);
+            ++rcount;
+          }
+          if (last_sub) {
+            // last TMEM read of this tile is done: hand the accumulator buffer back before the store
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[b]);
+          }
+          named_bar_sync(1 + q, 128);  // the quadrant's 32 x subw block is complete in staging
+          if (g == 0 && lane == 0) {
+            tma_store_5d(subw == 64 ? &tmO64 : &tmO32, ob, (int)ocol0, (int)(mb1 + qo1), (int)(mb2 + qo2),
+                         (int)(mb3 + qo3), 0);
+            tma_store_commit();
+            tma_store_wait_read0();  // staging buffer may be overwritten two sub-tiles from now
+          }
+          ++ocount;
+        }
+      } else {
+        // direct epilogue: fp32 outputs (tiny GEMMs: embeddings, conv_out)
+        for (uint32_t c0 = 16 * g; c0 < tile_out_w; c0 += 64) {
+          if (otile0 + c0 >= n_out) break;
+          uint32_t va[16], vg[16];
+          tmem_ld16(tlane + c0, va);
+          if (geglu) tmem_ld16(tlane + (uint32_t)(BN / 2) + c0, vg);
+          tmem_ld_wait();
+          if (!valid) continue;
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(va[j]);
+          const uint32_t ocol = otile0 + c0;
+          const bool full = (ocol + 16 <= n_out);
+          finish16(v, vg, n0 + c0, ocol, full);
+          if (p.res1 != nullptr) {
+            const __nv_bfloat16* rp = p.res1 + row * p.ld1 + ocol;
+            for (int j = 0; j < 16; ++j)
+              if (full || ocol + j < n_out) v[j] += p.s1 * __bfloat162float(rp[j]);
+          }
+          if (p.res2 != nullptr) {
+            const __nv_bfloat16* rp = p.res2 + row * p.ld2 + ocol;
+            for (int j = 0; j < 16; ++j)
+              if (full || ocol + j < n_out) v[j] += p.s2 * __bfloat162float(rp[j]);
+          }
+          if (p.out_fp32) {
+            float* op = reinterpret_cast<float*>(p.out) + row * p.ldo + ocol;
+            for (int j = 0; j < 16; ++j)
+              if (full || ocol + j < n_out) op[j] = v[j];
+          } else {
+            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldo + ocol;
+            for (int j = 0; j < 16; ++j)
+              if (full || ocol + j < n_out) op[j] = __float2bfloat16(v[j]);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[b]);
+      }
+    }
+    if (p.tma_epi && g == 0 && lane == 0) tma_store_wait_all();  // all bulk stores of this thread have landed
   }
 
   tc_fence_before();
@@ -300,6 +489,26 @@ static int ilog2_exact(uint32_t v) {
   return l;
 }
 
+// rank-5 view of a row-major [rows][ld] bf16 matrix addressed through the output-pixel space:
+// dims (cols, M1, M2, M3, 1), element (col, m1, m2, m3) at base + (m1*rs0 + m2*rs1 + m3*rs2)*ld + col
+static int encode_rows_view(CUtensorMap* tm, const void* base, int64_t ld, uint32_t cols, const uint32_t* m_ext,
+                            const int64_t* rs, const uint32_t* box_rows, uint32_t box_cols) {
+  uint64_t dims[5] = {cols, m_ext[0], m_ext[1], m_ext[2], 1};
+  uint64_t str[4];
+  for (int i = 0; i < 3; ++i) {
+    // a size-1 dim may carry any stride; keep it a positive multiple of 16 bytes
+    const int64_t s = (m_ext[i] > 1 ? rs[i] : 1) * ld * 2;
+    if (s <= 0) {
+      set_error("b200svd_gemm: output row strides must be positive");
+      return 1;
+    }
+    str[i] = (uint64_t)s;
+  }
+  str[3] = str[2] * (m_ext[2] ? m_ext[2] : 1);
+  uint32_t box[5] = {box_cols, box_rows[0], box_rows[1], box_rows[2], 1};
+  return box_cols == 64 ? encode_tmap_bf16(tm, base, 5, dims, str, box) : encode_tmap_bf16_sw64(tm, base, 5, dims, str, box);
+}
+
 template <int BN>
 static int launch(const b200svd_gemm_params* p, const CUtensorMap& tmA, const GemmDev& d, cudaStream_t st) {
   using Cfg = TileCfg<BN>;
@@ -311,18 +520,44 @@ static int launch(const b200svd_gemm_params* p, const CUtensorMap& tmA, const Ge
   if (encode_tmap_bf16(&tmB, p->w_ptr, 3, bd, bs, bb)) return 1;
   GemmDev dd = d;
   dd.n_tiles = (p->n + BN - 1) / BN;
+
+  // epilogue tensor maps: output (quadrant boxes of 32 rows) and residual-1 (full 128-row boxes)
+  CUtensorMap tmO64, tmO32, tmR64, tmR32;
+  memset(&tmO64, 0, sizeof(tmO64));
+  tmO32 = tmO64;
+  tmR64 = tmO64;
+  tmR32 = tmO64;
+  if (dd.tma_epi) {
+    const uint32_t n_out = p->act == B200SVD_ACT_GEGLU ? p->n / 2 : p->n;
+    const uint32_t b1 = p->m_box[0], b2 = p->m_box[1];
+    const uint32_t c1 = b1 < 32 ? b1 : 32;
+    const uint32_t c2 = (b2 < 32 / c1) ? b2 : 32 / c1;
+    const uint32_t c3 = 32 / (c1 * c2);
+    const uint32_t qbox[3] = {c1, c2, c3};
+    if (encode_rows_view(&tmO64, p->out, p->ldo, n_out, p->m_ext, p->out_rs, qbox, 64)) return 1;
+    if (encode_rows_view(&tmO32, p->out, p->ldo, n_out, p->m_ext, p->out_rs, qbox, 32)) return 1;
+    if (p->res1 != nullptr) {
+      if (encode_rows_view(&tmR64, p->res1, p->ld1, n_out, p->m_ext, p->out_rs, p->m_box, 64)) return 1;
+      if (encode_rows_view(&tmR32, p->res1, p->ld1, n_out, p->m_ext, p->out_rs, p->m_box, 32)) return 1;
+    }
+  }
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(mtgemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(mtgemm)");
     attr_set = true;
   }
-  const uint64_t grid = (uint64_t)dd.n_tiles * dd.m_tiles[0] * dd.m_tiles[1] * dd.m_tiles[2];
-  if (grid == 0 || grid > 0x7FFFFFFFull) {
-    set_error("mtgemm: bad grid size %llu", (unsigned long long)grid);
+  const uint64_t total = (uint64_t)dd.n_tiles * dd.m_tiles[0] * dd.m_tiles[1] * dd.m_tiles[2];
+  if (total == 0 || total > 0x7FFFFFFFull) {
+    set_error("mtgemm: bad tile count %llu", (unsigned long long)total);
     return 1;
   }
-  mtgemm_kernel<BN><<<(unsigned)grid, 192, Cfg::SMEM_BYTES, st>>>(tmA, tmB, dd);
+  const uint32_t sms = (uint32_t)sm_count();
+  const uint32_t grid = (uint32_t)(total < sms ? total : sms);
+  dd.total_tiles = (uint32_t)total;
+  dd.tiles_per_cta = (uint32_t)((total + grid - 1) / grid);
+  const uint32_t grid_used = (uint32_t)((total + dd.tiles_per_cta - 1) / dd.tiles_per_cta);
+  mtgemm_kernel<BN><<<grid_used, NUM_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, tmO64, tmO32, tmR64, tmR32, dd);
   B200_CHECK_LAUNCH("mtgemm launch");
   return 0;
 }
@@ -402,20 +637,30 @@ extern "C" int b200svd_gemm(const b200svd_gemm_params* p, void* stream) {
   d.s2 = p->s2;
 
   int bn = p->bn;
+  if (p->act == B200SVD_ACT_GEGLU) {
+    if (bn == 0) bn = 256;
+    if (bn != 256 || (p->n % 256) != 0) {
+      set_error("b200svd_gemm: GEGLU needs n (%u) divisible by 256 and the 256-wide tile (weights interleaved per tile)",
+                p->n);
+      return 1;
+    }
+  }
   if (bn == 0) {
     if (p->n <= 32) bn = 32;
     else if (p->n <= 64) bn = 64;
+    else if (p->n <= 128) bn = 128;
+    else if (p->n % 256 == 0) bn = 256;
     else if (p->n % 160 == 0) bn = 160;
-    else bn = 128;
+    else bn = 256;
   }
-  if (p->act == B200SVD_ACT_GEGLU && (p->n % bn) != 0) {
-    set_error("b200svd_gemm: GEGLU needs n (%u) divisible by the N tile (%d)", p->n, bn);
-    return 1;
-  }
-  const bool vec_ok = (p->ldo % 8 == 0) && (p->res1 == nullptr || p->ld1 % 8 == 0) &&
-                      (p->res2 == nullptr || p->ld2 % 8 == 0);
-  if (!vec_ok) {
-    set_error("b200svd_gemm: leading dimensions must be multiples of 8 elements");
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  d.tma_epi = (!p->out_fp32 && p->ldo % 8 == 0 && al16(p->out) &&
+               (p->res1 == nullptr || (p->ld1 % 8 == 0 && al16(p->res1))) &&
+               (p->res2 == nullptr || (p->ld2 % 8 == 0 && al16(p->res2))))
+                  ? 1
+                  : 0;
+  if (!d.tma_epi && !p->out_fp32) {
+    set_error("b200svd_gemm: bf16 outputs/residuals need 16-byte aligned bases and leading dims that are multiples of 8");
     return 1;
   }
 
@@ -427,6 +672,7 @@ extern "C" int b200svd_gemm(const b200svd_gemm_params* p, void* stream) {
     case 64: return launch<64>(p, tmA, d, st);
     case 128: return launch<128>(p, tmA, d, st);
     case 160: return launch<160>(p, tmA, d, st);
+    case 256: return launch<256>(p, tmA, d, st);
     default: set_error("b200svd_gemm: unsupported N tile %d", bn); return 1;
   }
 }

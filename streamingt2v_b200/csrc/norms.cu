@@ -35,7 +35,26 @@ __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx
 #pragma unroll
   for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
   const __nv_bfloat16* base = x + ((int64_t)n * P) * ldx + v * 8;
-  for (int p = p0 + r0; p < p1; p += rstep) {
+  constexpr int U = 4;  // independent 16-byte loads in flight per thread
+  int p = p0 + r0;
+  for (; p + (U - 1) * rstep < p1; p += U * rstep) {
+    uint4 u[U];
+#pragma unroll
+    for (int i = 0; i < U; ++i) u[i] = __ldg(reinterpret_cast<const uint4*>(base + (int64_t)(p + i * rstep) * ldx));
+#pragma unroll
+    for (int i = 0; i < U; ++i) {
+      const uint32_t w[4] = {u[i].x, u[i].y, u[i].z, u[i].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float a = bf16_lo(w[j]), b = bf16_hi(w[j]);
+        s[2 * j] += a;
+        q[2 * j] += a * a;
+        s[2 * j + 1] += b;
+        q[2 * j + 1] += b * b;
+      }
+    }
+  }
+  for (; p < p1; p += rstep) {
     const uint4 u = __ldg(reinterpret_cast<const uint4*>(base + (int64_t)p * ldx));
     const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
@@ -112,8 +131,7 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx
   }
   const __nv_bfloat16* xb = x + ((int64_t)n * P) * ldx + v * 8;
   __nv_bfloat16* yb = y + ((int64_t)n * P) * ldy + v * 8;
-  for (int p = p0 + r0; p < p1; p += rstep) {
-    const uint4 u = __ldg(reinterpret_cast<const uint4*>(xb + (int64_t)p * ldx));
+  auto apply8 = [&](const uint4& u) {
     const uint32_t w[4] = {u.x, u.y, u.z, u.w};
     uint32_t o[4];
 #pragma unroll
@@ -126,8 +144,19 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx
       }
       o[j] = pack_bf16x2(a, b);
     }
-    *reinterpret_cast<uint4*>(yb + (int64_t)p * ldy) = make_uint4(o[0], o[1], o[2], o[3]);
+    return make_uint4(o[0], o[1], o[2], o[3]);
+  };
+  constexpr int U = 4;
+  int p = p0 + r0;
+  for (; p + (U - 1) * rstep < p1; p += U * rstep) {
+    uint4 u[U];
+#pragma unroll
+    for (int i = 0; i < U; ++i) u[i] = __ldg(reinterpret_cast<const uint4*>(xb + (int64_t)(p + i * rstep) * ldx));
+#pragma unroll
+    for (int i = 0; i < U; ++i) *reinterpret_cast<uint4*>(yb + (int64_t)(p + i * rstep) * ldy) = apply8(u[i]);
   }
+  for (; p < p1; p += rstep)
+    *reinterpret_cast<uint4*>(yb + (int64_t)p * ldy) = apply8(__ldg(reinterpret_cast<const uint4*>(xb + (int64_t)p * ldx)));
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -215,18 +244,112 @@ __global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, int64_t ld
   }
 }
 
-static int gn_geometry(int C, int P, int* threads, int* rows_per_chunk, int* chunks) {
+// Fast path for C = 40*LPR channels-vectors (C = 320, 640, 1280): LPR lanes own one row, 5 x 16-byte vectors each,
+// all loads issued before first use; 32/LPR rows per warp.
+template <int LPR>
+__global__ void __launch_bounds__(256) layernorm5_kernel(
+    const __nv_bfloat16* __restrict__ x, int64_t ldx, __nv_bfloat16* __restrict__ y, int64_t ldy, int64_t rows, int C,
+    const float* __restrict__ gamma, const float* __restrict__ beta, float eps, const float* __restrict__ fvec,
+    int64_t ldf, int rows_per_frame, __nv_bfloat16* __restrict__ xsum, int64_t ldxs, int apply_silu) {
+  constexpr int RPW = 32 / LPR;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / LPR, li = lane % LPR;
+  const int64_t row = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + sub;
+  const bool active = row < rows;
+  const int64_t rr = active ? row : rows - 1;
+  const __nv_bfloat16* xr = x + rr * ldx;
+  uint4 u[5];
+#pragma unroll
+  for (int i = 0; i < 5; ++i) u[i] = __ldg(reinterpret_cast<const uint4*>(xr + (li + i * LPR) * 8));
+  float val[5][8];
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    const uint32_t w[4] = {u[i].x, u[i].y, u[i].z, u[i].w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      val[i][2 * j] = bf16_lo(w[j]);
+      val[i][2 * j + 1] = bf16_hi(w[j]);
+    }
+  }
+  if (fvec != nullptr) {
+    const float* fr = fvec + (rr / rows_per_frame) * ldf;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      const float4 f0 = __ldg(reinterpret_cast<const float4*>(fr + (li + i * LPR) * 8));
+      const float4 f1 = __ldg(reinterpret_cast<const float4*>(fr + (li + i * LPR) * 8) + 1);
+      val[i][0] += f0.x; val[i][1] += f0.y; val[i][2] += f0.z; val[i][3] += f0.w;
+      val[i][4] += f1.x; val[i][5] += f1.y; val[i][6] += f1.z; val[i][7] += f1.w;
+      if (xsum != nullptr) {
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] = pack_bf16x2(val[i][2 * j], val[i][2 * j + 1]);
+        if (active) *reinterpret_cast<uint4*>(xsum + row * ldxs + (li + i * LPR) * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          val[i][2 * j] = bf16_lo(o[j]);
+          val[i][2 * j + 1] = bf16_hi(o[j]);
+        }
+      }
+    }
+  }
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 5; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sum += val[i][j];
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / (float)C;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < 5; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float d = val[i][j] - mean;
+      sq += d * d;
+    }
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  const float rstd = rsqrtf(sq / (float)C + eps);
+  if (!active) return;
+  __nv_bfloat16* yr = y + row * ldy;
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    const int c0 = (li + i * LPR) * 8;
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c0)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c0) + 1);
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c0)), b1 = __ldg(reinterpret_cast<const float4*>(beta + c0) + 1);
+    const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    float o8[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float t = (val[i][j] - mean) * rstd * gg[j] + bb[j];
+      if (apply_silu) t = silu_f(t);
+      o8[j] = t;
+    }
+    *reinterpret_cast<uint4*>(yr + c0) = make_uint4(pack_bf16x2(o8[0], o8[1]), pack_bf16x2(o8[2], o8[3]),
+                                                     pack_bf16x2(o8[4], o8[5]), pack_bf16x2(o8[6], o8[7]));
+  }
+}
+
+static int gn_geometry(int C, int64_t n, int P, int* threads, int* rows_per_chunk, int* chunks) {
   if (C % 8 != 0 || C % 32 != 0) return 1;
   const int vecs = C / 8;
   if (vecs > 1024) return 1;
   int rpi = 256 / vecs;
   if (rpi < 1) rpi = 1;
   *threads = vecs * rpi;
-  // ~2 waves of CTAs over the GPU per sample batch is plenty; keep chunks >= 64 rows
-  int rpc = 256;
-  if (P < rpc) rpc = P;
-  *rows_per_chunk = rpc;
-  *chunks = (P + rpc - 1) / rpc;
+  // Enough CTAs to cover the GPU several times over (these kernels are latency-bound otherwise): aim for
+  // >= 8 CTAs per SM, but never less than one 4-deep unrolled batch of rows per thread, never more than 256 rows.
+  const int min_rpc = rpi * 4;
+  const int64_t target_ctas = (int64_t)sm_count() * 8;
+  int64_t rpc = ((int64_t)P * n + target_ctas - 1) / target_ctas;
+  rpc = ((rpc + min_rpc - 1) / min_rpc) * min_rpc;
+  if (rpc < min_rpc) rpc = min_rpc;
+  if (rpc > 256) rpc = 256 / min_rpc * min_rpc > 0 ? 256 / min_rpc * min_rpc : min_rpc;
+  if (rpc > P) rpc = P;
+  *rows_per_chunk = (int)rpc;
+  *chunks = (int)((P + rpc - 1) / rpc);
   return 0;
 }
 
@@ -239,7 +362,7 @@ extern "C" {
 int64_t b200svd_gn_scratch_doubles(int64_t n, int64_t p, int c) {
   using namespace b200;
   int threads, rpc, chunks;
-  if (gn_geometry(c, (int)p, &threads, &rpc, &chunks)) return -1;
+  if (gn_geometry(c, n, (int)p, &threads, &rpc, &chunks)) return -1;
   return n * (int64_t)chunks * 64;
 }
 
@@ -247,7 +370,7 @@ int b200svd_gn_stats(const void* x, int64_t ldx, int64_t n, int64_t p, int c, vo
                      void* counters, void* stream) {
   using namespace b200;
   int threads, rpc, chunks;
-  if (gn_geometry(c, (int)p, &threads, &rpc, &chunks)) {
+  if (gn_geometry(c, n, (int)p, &threads, &rpc, &chunks)) {
     set_error("gn_stats: unsupported channel count %d (need multiple of 32, <= 8192)", c);
     return 1;
   }
@@ -276,7 +399,7 @@ int b200svd_gn_apply(const void* x, int64_t ldx, void* y, int64_t ldy, int64_t n
                      const float* gamma, const float* beta, float eps, int apply_silu, void* stream) {
   using namespace b200;
   int threads, rpc, chunks;
-  if (gn_geometry(c, (int)p, &threads, &rpc, &chunks)) {
+  if (gn_geometry(c, n, (int)p, &threads, &rpc, &chunks)) {
     set_error("gn_apply: unsupported channel count %d", c);
     return 1;
   }
@@ -313,6 +436,21 @@ int b200svd_layernorm(const void* x, int64_t ldx, void* y, int64_t ldy, int64_t 
   __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(y);
   __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(xsum);
   if (rows_per_frame <= 0) rows_per_frame = 1;
+  const bool f_ok = (fvec == nullptr) || (ldf % 4 == 0 && (reinterpret_cast<uintptr_t>(fvec) & 15) == 0);
+  const bool gb_ok = ((reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta)) & 15) == 0;
+  if ((c == 320 || c == 640 || c == 1280) && f_ok && gb_ok) {
+    const int lpr = c / 40;
+    const int rpw = 32 / lpr;
+    const unsigned g5 = (unsigned)((rows + (int64_t)wpb * rpw - 1) / ((int64_t)wpb * rpw));
+    if (lpr == 8)
+      layernorm5_kernel<8><<<g5, wpb * 32, 0, st>>>(xp, ldx, yp, ldy, rows, c, gamma, beta, eps, fvec, ldf, rows_per_frame, xs, ldxs, apply_silu);
+    else if (lpr == 16)
+      layernorm5_kernel<16><<<g5, wpb * 32, 0, st>>>(xp, ldx, yp, ldy, rows, c, gamma, beta, eps, fvec, ldf, rows_per_frame, xs, ldxs, apply_silu);
+    else
+      layernorm5_kernel<32><<<g5, wpb * 32, 0, st>>>(xp, ldx, yp, ldy, rows, c, gamma, beta, eps, fvec, ldf, rows_per_frame, xs, ldxs, apply_silu);
+    B200_CHECK_LAUNCH("layernorm5");
+    return 0;
+  }
 #define LN_LAUNCH(MV)                                                                                              \
   layernorm_kernel<MV><<<grid, wpb * 32, 0, st>>>(xp, ldx, yp, ldy, rows, c, gamma, beta, eps, fvec, ldf,          \
                                                   rows_per_frame, xs, ldxs, apply_silu)

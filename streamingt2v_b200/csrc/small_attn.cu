@@ -45,33 +45,41 @@ __global__ void __launch_bounds__(SA_WARPS * 32) small_attn_kernel(const SmallAt
   const int s = (int)(bs % p.S);
   const int b = (int)(bs / p.S);
 
-  // stage K, V (Lk rows x 128 B): lane -> (row = lane/8 + 4*it, 16-byte chunk = lane%8)
+  // stage K, V (Lk rows x 128 B) with cp.async so that the Q loads below overlap them:
+  // lane -> (row = lane/8 + 4*it, 16-byte chunk = lane%8)
   {
     const int chunk = lane & 7;
     for (int j = lane >> 3; j < p.Lk; j += 4) {
       const int64_t row = ((int64_t)b * p.Lk + j) * p.Skv + (int64_t)s * p.kv_pp;
-      const uint4 kk = __ldg(reinterpret_cast<const uint4*>(p.k + row * p.ldk + h * 64) + chunk);
-      const uint4 vv = __ldg(reinterpret_cast<const uint4*>(p.v + row * p.ldv + h * 64) + chunk);
-      *(reinterpret_cast<uint4*>(&ks[warp][j][0]) + chunk) = kk;
-      *(reinterpret_cast<uint4*>(&vs[warp][j][0]) + chunk) = vv;
+      const void* gk = reinterpret_cast<const uint4*>(p.k + row * p.ldk + h * 64) + chunk;
+      const void* gv = reinterpret_cast<const uint4*>(p.v + row * p.ldv + h * 64) + chunk;
+      const uint32_t sk = smem_u32(reinterpret_cast<uint4*>(&ks[warp][j][0]) + chunk);
+      const uint32_t sv = smem_u32(reinterpret_cast<uint4*>(&vs[warp][j][0]) + chunk);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sk), "l"(gk) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sv), "l"(gv) : "memory");
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
   }
-  __syncwarp();
-  if (lane >= p.Lq) return;
-
-  const int64_t qrow = ((int64_t)b * p.Lq + lane) * p.S + s;
+  const int qi = lane < p.Lq ? lane : p.Lq - 1;  // idle lanes shadow the last query (no divergence on the loads)
+  const int64_t qrow = ((int64_t)b * p.Lq + qi) * p.S + s;
   uint32_t qp[32];
   {
     const uint4* qsrc = reinterpret_cast<const uint4*>(p.q + qrow * p.ldq + h * 64);
+    uint4 u[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) u[c] = __ldg(qsrc + c);
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
-      const uint4 u = __ldg(qsrc + c);
-      qp[4 * c] = u.x;
-      qp[4 * c + 1] = u.y;
-      qp[4 * c + 2] = u.z;
-      qp[4 * c + 3] = u.w;
+      qp[4 * c] = u[c].x;
+      qp[4 * c + 1] = u[c].y;
+      qp[4 * c + 2] = u[c].z;
+      qp[4 * c + 3] = u[c].w;
     }
   }
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  __syncwarp();
+  if (lane >= p.Lq) return;
+
   float sc[SA_MAXL];
   float mx = -INFINITY;
 #pragma unroll

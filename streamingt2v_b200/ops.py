@@ -38,13 +38,33 @@ class profile:
         recs, _PROFILE = _PROFILE, None
         torch.cuda.synchronize()
         self.families = {}
+        self.launch_records = []  # (family, desc, ms, flops)
         for fam, flops, nbytes, e0, e1 in recs:
+            desc = ""
+            if isinstance(fam, tuple):
+                fam, desc = fam
+            self.launch_records.append((fam, desc, e0.elapsed_time(e1), flops))
             f = self.families.setdefault(fam, dict(launches=0, ms=0.0, flops=0.0, bytes=0.0))
             f["launches"] += 1
             f["ms"] += e0.elapsed_time(e1)
             f["flops"] += flops
             f["bytes"] += nbytes
         return False
+
+
+def summarize_records(records, family="mtgemm", top=40):
+    """Group per-launch records by descriptor: [(desc, launches, total ms, TFLOP/s)] sorted by total time."""
+    agg = {}
+    for fam, desc, ms, flops in records:
+        if fam != family:
+            continue
+        a = agg.setdefault(desc, [0, 0.0, 0.0])
+        a[0] += 1
+        a[1] += ms
+        a[2] += flops
+    rows = [(d, v[0], v[1], v[2] / max(v[1], 1e-9) / 1e9) for d, v in agg.items()]
+    rows.sort(key=lambda r: -r[2])
+    return rows[:top]
 
 
 def _prof_begin():
@@ -136,7 +156,9 @@ def gemm_raw(*, a, a_dims, a_strides, a_box, w, n, k, taps, tap_off, m_ext, m_bo
         n_out = n // 2 if act == ACT_GEGLU else n
         nbytes = 2.0 * rows * k + 2.0 * taps * n * k + (4.0 if out_fp32 else 2.0) * rows * n_out
         nbytes += 2.0 * rows * n_out * ((res1 is not None) + (res2 is not None))
-        _prof_end(e0, "mtgemm", 2.0 * rows * k * n * taps, nbytes)
+        desc = (f"M{rows} K{k} N{n} taps{taps} act{act} res{(res1 is not None) + (res2 is not None)} "
+                f"fvec{int(fvec is not None)} f32{int(out_fp32)} box{tuple(int(b) for b in m_box)}")
+        _prof_end(e0, ("mtgemm", desc), 2.0 * rows * k * n * taps, nbytes)
 
 
 def _epi_kwargs(rows, n_out, out, bias, fvec, rows_per_frame, act, s_acc, res1, s1, res2, s2, out_fp32):

@@ -46,11 +46,10 @@ def pack_tconv3(w: torch.Tensor, device) -> torch.Tensor:
 
 
 def geglu_tile(n2: int) -> int:
-    """N tile used for a GEGLU projection with 2F = n2 output rows (must divide n2; halves are multiples of 16)."""
-    for bn in (160, 128, 64, 32):
-        if n2 % bn == 0:
-            return bn
-    raise ValueError(f"GEGLU width {n2} not tileable")
+    """N tile of a GEGLU projection with 2F = n2 output rows: the kernel's 256-wide tile (128 value + 128 gate)."""
+    if n2 % 256 != 0:
+        raise ValueError(f"GEGLU width {n2} must be a multiple of 256")
+    return 256
 
 
 def pack_geglu(w: torch.Tensor, b: torch.Tensor, device):
