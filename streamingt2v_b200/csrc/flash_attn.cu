@@ -1,18 +1,24 @@
-// FlashAttention forward for sm_100a, head dim 64: tcgen05.mma (S = Q K^T and O_blk = P V, accumulators in TMEM),
-// TMA-fed Q/K/V tiles read straight from the fused QKV projection output [(n s), 3C] (no head split / transpose
-// in HBM), online softmax in registers (one query row per thread).
+// FlashAttention forward for sm_100a, head dim 64 (v2): tcgen05.mma for S = Q K^T and O += P V with all
+// accumulators in TMEM, TMA-fed Q/K/V tiles read straight from the fused QKV projection output [(n s), 3C]
+// (no head split / transpose in HBM).
 //
 // Replaces the spatial self-attention core of BasicTransformerBlock.attn1
 // (reference code/models/svd/sgm/modules/attention.py:320-351 SDPA / :427-446 xformers), batch = frames,
 // heads = C/64, sequence = H*W.
 //
-// CTA = 128 query rows of one (frame, head); 6 warps: warp0 TMA producer, warp1 MMA issuer + TMEM owner,
-// warps 2..5 softmax/correction/epilogue.  Per 128-key block:
-//   MMA : S[128x128] = Q K_j^T                      (4 x tcgen05.mma M128 N128 K16, K-major A and B)
-//   SM  : m,l update; P = exp2(S*c - m*c) -> bf16 into smem (128B-swizzled K-major A tile)
-//   MMA : O_blk[128x64] = P V_j                     (8 x tcgen05.mma M128 N64 K16, B = V is MN-major)
-//   SM  : O = O*alpha + O_blk                        (registers)
-// Two CTAs co-reside per SM so one CTA's softmax overlaps the other's MMAs.
+// CTA = TWO 128-row query tiles (A, B) of one (frame, head), ping-ponged so the tensor core works on one tile
+// while the other tile's softmax runs; K/V blocks are loaded once per CTA and shared by both tiles.
+//   warp 0      TMA producer (Q_A, Q_B once; K/V ring of 4 stages)
+//   warp 1      MMA issuer + TMEM owner
+//   warps 2..9  softmax: 4 warps per query tile, one query row per thread
+// Per 128-key block and tile:
+//   MMA : S[128x128] = Q K_j^T                       (4 x tcgen05.mma M128 N128 K16, fp32 in TMEM)
+//   SM  : one pass over the row in registers: block max, lazy running-max update, P = exp2(S*c - m*c),
+//         P written back to TMEM as packed bf16 over the S columns (no shared-memory round trip)
+//   MMA : O[128x64] += P V_j                         (8 x tcgen05.mma, A = P from TMEM, B = V MN-major from smem)
+// O stays in TMEM for the whole KV loop.  The running max is only raised when a block max exceeds it by more than
+// 2^8 (then O and l are rescaled once, by the same softmax threads); probabilities are therefore bounded by 2^8
+// instead of 1, which bf16 represents exactly as well, and the final O / l is unchanged.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <math.h>
@@ -26,12 +32,13 @@ namespace b200 {
 constexpr int FA_BQ = 128;
 constexpr int FA_BK = 128;
 constexpr int FA_D = 64;
-constexpr int FA_KV_STAGES = 2;
-constexpr int FA_Q_BYTES = FA_BQ * FA_D * 2;        // 16 KB
+constexpr int FA_KV_STAGES = 4;
+constexpr int FA_Q_BYTES = FA_BQ * FA_D * 2;        // 16 KB per query tile
 constexpr int FA_KV_TILE_BYTES = FA_BK * FA_D * 2;  // 16 KB each for K and V
-constexpr int FA_P_BYTES = FA_BQ * FA_BK * 2;       // 32 KB (two 64-column swizzled sub-tiles)
-constexpr int FA_SMEM_BYTES = FA_Q_BYTES + FA_KV_STAGES * 2 * FA_KV_TILE_BYTES + FA_P_BYTES + 128;  // 2 CTAs / SM
-constexpr int FA_TMEM_COLS = 256;  // S: cols [0,128), O_blk: cols [128,192)
+constexpr int FA_SMEM_BYTES = 2 * FA_Q_BYTES + FA_KV_STAGES * 2 * FA_KV_TILE_BYTES + 256;
+constexpr int FA_TMEM_COLS = 512;  // S_A [0,128) S_B [128,256) (P aliases the first 64 columns), O_A [256,320) O_B [320,384)
+constexpr int FA_THREADS = 10 * 32;
+constexpr float FA_RESCALE_THRESHOLD = 8.0f;  // log2 units
 
 struct FaParams {
   __nv_bfloat16* out;
@@ -40,25 +47,24 @@ struct FaParams {
   float scale_log2;
 };
 
-__global__ void __launch_bounds__(192, 2)
+__global__ void __launch_bounds__(FA_THREADS, 1)
 flash_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const FaParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];  // SWIZZLE_128B tiles need 1024-byte alignment
   if ((smem_u32(smem) & 1023u) != 0) __trap();
-  uint8_t* sQ = smem;
-  uint8_t* sKV = sQ + FA_Q_BYTES;                          // stage s: K at sKV + s*32K, V at +16K
-  uint8_t* sP = sKV + FA_KV_STAGES * 2 * FA_KV_TILE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + FA_P_BYTES);
+  uint8_t* sQ = smem;                      // tile X at sQ + X*16K
+  uint8_t* sKV = sQ + 2 * FA_Q_BYTES;      // stage s: K at sKV + s*32K, V at +16K
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + FA_KV_STAGES * 2 * FA_KV_TILE_BYTES);
   uint64_t* q_full = bars;
-  uint64_t* kv_full = bars + 1;                  // [2]
-  uint64_t* kv_empty = bars + 3;                 // [2]
-  uint64_t* s_full = bars + 5;
-  uint64_t* p_full = bars + 6;
-  uint64_t* o_full = bars + 7;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* kv_full = bars + 1;                       // [4]
+  uint64_t* kv_empty = kv_full + FA_KV_STAGES;        // [4]
+  uint64_t* s_full = kv_empty + FA_KV_STAGES;         // [2]
+  uint64_t* p_full = s_full + 2;                      // [2]
+  uint64_t* pv_done = p_full + 2;                     // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q_tile = blockIdx.x, head = blockIdx.y, n = blockIdx.z;
-  const int q0 = q_tile * FA_BQ;
+  const int head = blockIdx.y, n = blockIdx.z;
+  const int q0 = blockIdx.x * (2 * FA_BQ);
   const int nkb = (p.S + FA_BK - 1) / FA_BK;
 
   if (warp == 0 && lane == 0) {
@@ -68,9 +74,11 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const FaParams p) {
       mbar_init(&kv_full[s], 1);
       mbar_init(&kv_empty[s], 1);
     }
-    mbar_init(s_full, 1);
-    mbar_init(p_full, 128);
-    mbar_init(o_full, 1);
+    for (int x = 0; x < 2; ++x) {
+      mbar_init(&s_full[x], 1);
+      mbar_init(&p_full[x], 4);  // one arrive per softmax warp of the tile
+      mbar_init(&pv_done[x], 1);
+    }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -81,14 +89,13 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const FaParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_S = tmem_base;
-  const uint32_t tmem_O = tmem_base + 128;
 
   if (warp == 0) {
     if (lane == 0) {
       // ===================== TMA producer =====================
-      mbar_expect_tx(q_full, FA_Q_BYTES);
+      mbar_expect_tx(q_full, 2 * FA_Q_BYTES);
       tma_load_3d(sQ, &tmQKV, q_full, head * FA_D, q0, n);
+      tma_load_3d(sQ + FA_Q_BYTES, &tmQKV, q_full, head * FA_D, q0 + FA_BQ, n);
       for (int j = 0; j < nkb; ++j) {
         const int s = j % FA_KV_STAGES;
         const uint32_t ph = (j / FA_KV_STAGES) & 1;
@@ -104,142 +111,175 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const FaParams p) {
       // ===================== MMA issuer =====================
       constexpr uint32_t idesc_qk = make_idesc_f16(128, 128, 1, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc_f16(128, 64, 1, 0, 1);  // B (=V) is MN-major
-      const uint64_t qdesc = smem_desc_k_sw128(smem_u32(sQ));
-      const uint64_t pdesc0 = smem_desc_k_sw128(smem_u32(sP));
-      const uint64_t pdesc1 = smem_desc_k_sw128(smem_u32(sP + FA_BQ * 128));
+      const uint64_t qdesc[2] = {smem_desc_k_sw128(smem_u32(sQ)), smem_desc_k_sw128(smem_u32(sQ + FA_Q_BYTES))};
       mbar_wait(q_full, 0);
-      // S(0)
       mbar_wait(&kv_full[0], 0);
       tc_fence_after();
       {
         const uint64_t kdesc = smem_desc_k_sw128(smem_u32(sKV));
+        for (int x = 0; x < 2; ++x) {
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) umma_f16_ss(tmem_S, qdesc + kk * 2, kdesc + kk * 2, idesc_qk, kk > 0);
-        umma_commit(s_full);
+          for (int kk = 0; kk < 4; ++kk)
+            umma_f16_ss(tmem_base + x * 128, qdesc[x] + kk * 2, kdesc + kk * 2, idesc_qk, kk > 0);
+          umma_commit(&s_full[x]);
+        }
       }
       for (int j = 0; j < nkb; ++j) {
-        const int s = j % FA_KV_STAGES;
-        // P(j) ready (and S(j) fully read by the softmax warps)
-        mbar_wait(p_full, j & 1);
-        tc_fence_after();
-        const uint64_t vdesc = smem_desc_mn_sw128(smem_u32(sKV + s * 2 * FA_KV_TILE_BYTES + FA_KV_TILE_BYTES));
-#pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {
-          const uint64_t pd = (kk < 4 ? pdesc0 : pdesc1) + (uint64_t)((kk & 3) * 2);
-          // V: 16 keys per MMA = 2 swizzle row-groups of 1024 B -> +2048 B = +128 in the (addr>>4) field
-          umma_f16_ss(tmem_O, pd, vdesc + (uint64_t)(kk * 128), idesc_pv, kk > 0);
-        }
-        umma_commit(o_full);
-        umma_commit(&kv_empty[s]);
-        if (j + 1 < nkb) {
-          const int s1 = (j + 1) % FA_KV_STAGES;
-          mbar_wait(&kv_full[s1], ((j + 1) / FA_KV_STAGES) & 1);
+        const int st = j % FA_KV_STAGES;
+        const uint64_t vdesc = smem_desc_mn_sw128(smem_u32(sKV + st * 2 * FA_KV_TILE_BYTES + FA_KV_TILE_BYTES));
+        for (int x = 0; x < 2; ++x) {
+          // P_x(j) is in TMEM (and S_x(j) fully consumed)
+          mbar_wait(&p_full[x], j & 1);
           tc_fence_after();
-          const uint64_t kdesc = smem_desc_k_sw128(smem_u32(sKV + s1 * 2 * FA_KV_TILE_BYTES));
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) umma_f16_ss(tmem_S, qdesc + kk * 2, kdesc + kk * 2, idesc_qk, kk > 0);
-          umma_commit(s_full);
+          for (int kk = 0; kk < 8; ++kk) {
+            // A = P from TMEM: 16 bf16 of K per MMA = 8 packed 32-bit columns; V: +2048 B (= +128 in addr>>4) per 16 keys
+            umma_f16_ts(tmem_base + 256 + x * 64, tmem_base + x * 128 + kk * 8, vdesc + (uint64_t)(kk * 128), idesc_pv,
+                        (j > 0 || kk > 0) ? 1u : 0u);
+          }
+          umma_commit(&pv_done[x]);
+          if (x == 1) umma_commit(&kv_empty[st]);
+          if (j + 1 < nkb) {
+            const int s1 = (j + 1) % FA_KV_STAGES;
+            if (x == 0) {
+              mbar_wait(&kv_full[s1], ((j + 1) / FA_KV_STAGES) & 1);
+              tc_fence_after();
+            }
+            const uint64_t kdesc = smem_desc_k_sw128(smem_u32(sKV + s1 * 2 * FA_KV_TILE_BYTES));
+            // executes after PV_x(j) in the tensor pipe (issue order), which was the last reader of P_x(j)
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              umma_f16_ss(tmem_base + x * 128, qdesc[x] + kk * 2, kdesc + kk * 2, idesc_qk, kk > 0);
+            umma_commit(&s_full[x]);
+          }
         }
       }
     }
     __syncwarp();
   } else {
-    // ===================== softmax / correction / epilogue warps =====================
+    // ===================== softmax warps: tile x = (warp-2)/4, TMEM lane quadrant = warp % 4 =====================
+    const int x = (warp - 2) >> 2;
     const int qd = warp & 3;
     const int r = qd * 32 + lane;  // query row in tile == TMEM lane
     const uint32_t tl = ((uint32_t)(qd * 32)) << 16;
-    float o_acc[FA_D];
-#pragma unroll
-    for (int d = 0; d < FA_D; ++d) o_acc[d] = 0.f;
-    float m_run = -INFINITY, l_run = 0.f;
-    uint8_t* prow = sP + r * 128;
-    const int sw = r & 7;
+    const uint32_t tS = tmem_base + x * 128 + tl;
+    const uint32_t tO = tmem_base + 256 + x * 64 + tl;
+    float m_used = -INFINITY, l_run = 0.f;
+    const float c = p.scale_log2;
 
     for (int j = 0; j < nkb; ++j) {
-      mbar_wait(s_full, j & 1);
+      mbar_wait(&s_full[x], j & 1);
       tc_fence_after();
+      // pass 1 over the row (TMEM reads are cheap; keeping all 128 scores live would exceed the 168-register
+      // budget that 10 warps per CTA leave per thread): block max
       const int kbase = j * FA_BK;
-      const bool tail = (kbase + FA_BK > p.S);
-      // pass 1: row max
-      float mx = m_run;
+      const bool tail = kbase + FA_BK > p.S;
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
       for (int c0 = 0; c0 < FA_BK; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_S + tl + c0, v);
+        uint32_t sv[32];
+        tmem_ld32(tS + c0, sv);
         tmem_ld_wait();
+        if (tail) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float sv = __uint_as_float(v[i]);
-          if (tail && kbase + c0 + i >= p.S) sv = -INFINITY;
-          mx = fmaxf(mx, sv);
+          for (int i = 0; i < 32; ++i)
+            if (kbase + c0 + i >= p.S) sv[i] = 0xff800000u;  // -inf
+        }
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          mx0 = fmaxf(mx0, __uint_as_float(sv[i]));
+          mx1 = fmaxf(mx1, __uint_as_float(sv[i + 1]));
+          mx2 = fmaxf(mx2, __uint_as_float(sv[i + 2]));
+          mx3 = fmaxf(mx3, __uint_as_float(sv[i + 3]));
         }
       }
-      const float m_new = mx;  // finite: every block has >= 1 valid key
-      const float alpha = exp2f((m_run - m_new) * p.scale_log2);
-      const float mb = m_new * p.scale_log2;
-      float lsum = 0.f;
-      // pass 2: P = exp2(S*c - m*c) -> bf16 -> swizzled smem
+      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      if (j == 0) {
+        m_used = mx;
+      } else {
+        const bool need = (mx - m_used) * c > FA_RESCALE_THRESHOLD;
+        if (__any_sync(0xffffffffu, need)) {
+          // rare: raise the running max and rescale O (in TMEM) and l once
+          mbar_wait(&pv_done[x], (j - 1) & 1);  // PV(j-1) has been accumulated
+          tc_fence_after();
+          const float m_new = need ? mx : m_used;
+          const float alpha = exp2f((m_used - m_new) * c);
+          uint32_t ov[32];
+#pragma unroll
+          for (int c0 = 0; c0 < FA_D; c0 += 32) {
+            tmem_ld32(tO + c0, ov);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
+            tmem_st32(tO + c0, ov);
+          }
+          tmem_st_wait();
+          l_run *= alpha;
+          m_used = m_new;
+        }
+      }
+      const float mb = m_used * c;
+      float l0 = 0.f, l1 = 0.f;
+      // pass 2: P = exp2(S*c - m*c), packed bf16x2, written back over the S columns (first 64 of the tile's 128).
+      // All 128 scores are read before any P column is written (P aliases S).
+      uint32_t pk[64];
 #pragma unroll
       for (int c0 = 0; c0 < FA_BK; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_S + tl + c0, v);
+        uint32_t sv[32];
+        tmem_ld32(tS + c0, sv);
         tmem_ld_wait();
-        uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          float a = __uint_as_float(v[2 * i]), b = __uint_as_float(v[2 * i + 1]);
-          a = exp2f(fmaf(a, p.scale_log2, -mb));
-          b = exp2f(fmaf(b, p.scale_log2, -mb));
+          float a = ex2_approx(fmaf(__uint_as_float(sv[2 * i]), c, -mb));
+          float b = ex2_approx(fmaf(__uint_as_float(sv[2 * i + 1]), c, -mb));
           if (tail) {
             if (kbase + c0 + 2 * i >= p.S) a = 0.f;
             if (kbase + c0 + 2 * i + 1 >= p.S) b = 0.f;
           }
-          // accumulate the row sum from the bf16-rounded values that the PV MMA will actually use
-          const uint32_t w = pack_bf16x2(a, b);
-          pk[i] = w;
-          lsum += bf16_lo(w) + bf16_hi(w);
-        }
-        // 32 columns = 4 x 16-byte chunks; sub-tile = c0/64, chunk index within the 128-byte row = (c0%64)/8 + q
-        uint8_t* sub = prow + (c0 >> 6) * (FA_BQ * 128);
-        const int cb = (c0 & 63) >> 3;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int chunk = (cb + q) ^ sw;
-          *reinterpret_cast<uint4*>(sub + chunk * 16) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+          l0 += a;
+          l1 += b;
+          pk[(c0 >> 1) + i] = pack_bf16x2(a, b);
         }
       }
-      l_run = l_run * alpha + lsum;
-      m_run = m_new;
-      // publish P (generic-proxy smem writes -> async proxy) and release S
-      fence_proxy_async_smem();
+      {
+        uint32_t t0[32], t1[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          t0[i] = pk[i];
+          t1[i] = pk[32 + i];
+        }
+        tmem_st32(tS + 0, t0);
+        tmem_st32(tS + 32, t1);
+      }
+      l_run += l0 + l1;
+      tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(p_full);
-      // rescale running output while the PV MMA runs
-#pragma unroll
-      for (int d = 0; d < FA_D; ++d) o_acc[d] *= alpha;
-      mbar_wait(o_full, j & 1);
-      tc_fence_after();
-#pragma unroll
-      for (int c0 = 0; c0 < FA_D; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_O + tl + c0, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o_acc[c0 + i] += __uint_as_float(v[i]);
-      }
-      tc_fence_before();  // order these TMEM reads before the next arrive (p_full) that lets PV(j+1) overwrite O
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[x]);
     }
-    // epilogue: normalise and store 64 bf16 (128 B contiguous) per row
-    if (q0 + r < p.S) {
-      const float inv = 1.0f / l_run;
-      __nv_bfloat16* dst = p.out + ((int64_t)n * p.S + q0 + r) * p.ldo + head * FA_D;
+    // epilogue: O / l -> bf16 -> 128 B contiguous per row
+    mbar_wait(&pv_done[x], (nkb - 1) & 1);
+    tc_fence_after();
+    const int qrow = q0 + x * FA_BQ + r;
+    const float inv = 1.0f / l_run;
+    uint32_t ova[32], ovb[32];
+    tmem_ld32(tO + 0, ova);
+    tmem_ld32(tO + 32, ovb);
+    tmem_ld_wait();
+    if (qrow < p.S) {
+      __nv_bfloat16* dst = p.out + ((int64_t)n * p.S + qrow) * p.ldo + head * FA_D;
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        reinterpret_cast<uint4*>(dst)[c] =
-            make_uint4(pack_bf16x2(o_acc[8 * c] * inv, o_acc[8 * c + 1] * inv),
-                       pack_bf16x2(o_acc[8 * c + 2] * inv, o_acc[8 * c + 3] * inv),
-                       pack_bf16x2(o_acc[8 * c + 4] * inv, o_acc[8 * c + 5] * inv),
-                       pack_bf16x2(o_acc[8 * c + 6] * inv, o_acc[8 * c + 7] * inv));
+      for (int cc = 0; cc < 4; ++cc) {
+        reinterpret_cast<uint4*>(dst)[cc] =
+            make_uint4(pack_bf16x2(__uint_as_float(ova[8 * cc]) * inv, __uint_as_float(ova[8 * cc + 1]) * inv),
+                       pack_bf16x2(__uint_as_float(ova[8 * cc + 2]) * inv, __uint_as_float(ova[8 * cc + 3]) * inv),
+                       pack_bf16x2(__uint_as_float(ova[8 * cc + 4]) * inv, __uint_as_float(ova[8 * cc + 5]) * inv),
+                       pack_bf16x2(__uint_as_float(ova[8 * cc + 6]) * inv, __uint_as_float(ova[8 * cc + 7]) * inv));
+        reinterpret_cast<uint4*>(dst)[4 + cc] =
+            make_uint4(pack_bf16x2(__uint_as_float(ovb[8 * cc]) * inv, __uint_as_float(ovb[8 * cc + 1]) * inv),
+                       pack_bf16x2(__uint_as_float(ovb[8 * cc + 2]) * inv, __uint_as_float(ovb[8 * cc + 3]) * inv),
+                       pack_bf16x2(__uint_as_float(ovb[8 * cc + 4]) * inv, __uint_as_float(ovb[8 * cc + 5]) * inv),
+                       pack_bf16x2(__uint_as_float(ovb[8 * cc + 6]) * inv, __uint_as_float(ovb[8 * cc + 7]) * inv));
       }
     }
   }
@@ -281,8 +321,8 @@ extern "C" int b200svd_flash_attn(const void* qkv, int64_t ldqkv, void* out, int
   p.heads = heads;
   p.C = C;
   p.scale_log2 = scale * 1.4426950408889634f;
-  dim3 grid((s + FA_BQ - 1) / FA_BQ, heads, n);
-  flash_attn_kernel<<<grid, 192, FA_SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream)>>>(tm, p);
+  dim3 grid((s + 2 * FA_BQ - 1) / (2 * FA_BQ), heads, n);
+  flash_attn_kernel<<<grid, FA_THREADS, FA_SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream)>>>(tm, p);
   B200_CHECK_LAUNCH("flash_attn");
   return 0;
 }
