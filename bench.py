@@ -269,8 +269,10 @@ def run_ours(args):
                        gbytes=round(v["bytes"] / 1e9, 3)) for k, v in prof.families.items()}
         if os.environ.get("B200SVD_BENCH_SHAPES"):
             with open(os.environ["B200SVD_BENCH_SHAPES"], "w") as fh:
-                for d_, n_, ms_, tf_ in ops.summarize_records(prof.launch_records, "mtgemm", 60):
-                    fh.write(f"{ms_:9.3f} ms n={n_:3d} avg={ms_ / n_:7.3f} {tf_:7.1f} TF/s  {d_}\n")
+                for famname in ("mtgemm", "flash_attn", "small_attn", "groupnorm", "layernorm"):
+                    fh.write(f"== {famname}\n")
+                    for d_, n_, ms_, tf_ in ops.summarize_records(prof.launch_records, famname, 60):
+                        fh.write(f"{ms_:9.3f} ms n={n_:3d} avg={ms_ / n_:7.3f} {tf_:7.1f} TF/s  {d_}\n")
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))

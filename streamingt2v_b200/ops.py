@@ -270,13 +270,15 @@ _FAMILY = {"b200svd_flash_attn": "flash_attn", "b200svd_small_attn": "small_attn
            "b200svd_gn_apply": "groupnorm", "b200svd_layernorm": "layernorm"}
 
 
-def _call(name, *args, flops=0.0, nbytes=0.0):
+def _call(name, *args, flops=0.0, nbytes=0.0, desc=""):
     global _launch_count
     lib = _lib.load()
     e0 = _prof_begin()
     _lib.check(getattr(lib, name)(*args), name)
     _launch_count += 1
-    _prof_end(e0, _FAMILY.get(name, "glue"), flops, nbytes)
+    if e0 is not None:
+        fam = _FAMILY.get(name, "glue")
+        _prof_end(e0, (fam, desc) if desc else fam, flops, nbytes)
 
 
 def flash_attn(qkv, n, s, heads, out=None):
@@ -287,7 +289,7 @@ def flash_attn(qkv, n, s, heads, out=None):
     if out is None:
         out = torch.empty((n * s, Cc), dtype=torch.bfloat16, device=qkv.device)
     _call("b200svd_flash_attn", _ptr(qkv), qkv.stride(0), _ptr(out), out.stride(0), n, s, heads, 64 ** -0.5, _stream(),
-          flops=4.0 * n * heads * float(s) * s * 64, nbytes=2.0 * n * s * 4 * Cc)
+          flops=4.0 * n * heads * float(s) * s * 64, nbytes=2.0 * n * s * 4 * Cc, desc=f"n{n} s{s} h{heads}")
     return out
 
 
@@ -301,7 +303,8 @@ def small_attn(q, k, v, *, b, s, heads, lq, lk, kv_per_pixel=True, out=None):
     _call("b200svd_small_attn", _ptr(q), q.stride(0), _ptr(k), k.stride(0), _ptr(v), v.stride(0), _ptr(out),
           out.stride(0), b, s, heads, lq, lk, 1 if kv_per_pixel else 0, 64 ** -0.5, _stream(),
           flops=4.0 * b * s * heads * lq * lk * 64,
-          nbytes=2.0 * Cc * (2 * b * lq * s + 2 * b * lk * (s if kv_per_pixel else 1)))
+          nbytes=2.0 * Cc * (2 * b * lq * s + 2 * b * lk * (s if kv_per_pixel else 1)),
+          desc=f"b{b} s{s} h{heads} {lq}x{lk} pp{int(kv_per_pixel)}")
     return out
 
 
@@ -336,9 +339,9 @@ def group_norm(x, n, p, gamma, beta, eps, *, silu=False, out=None, sums=None):
         raise _lib.B200Error(f"group_norm: unsupported channel count {Cc}")
     scratch, counters = _gn_scratch(x.device, need, n)
     _call("b200svd_gn_stats", _ptr(x), x.stride(0), n, p, Cc, _ptr(sums), _ptr(scratch), _ptr(counters), _stream(),
-          nbytes=2.0 * n * p * Cc)
+          nbytes=2.0 * n * p * Cc, desc=f"stats n{n} p{p} c{Cc}")
     _call("b200svd_gn_apply", _ptr(x), x.stride(0), _ptr(out), out.stride(0), n, p, Cc, _ptr(sums), _ptr(gamma),
-          _ptr(beta), float(eps), 1 if silu else 0, _stream(), nbytes=4.0 * n * p * Cc)
+          _ptr(beta), float(eps), 1 if silu else 0, _stream(), nbytes=4.0 * n * p * Cc, desc=f"apply n{n} p{p} c{Cc}")
     return out
 
 
@@ -350,7 +353,7 @@ def layer_norm(x, gamma, beta, eps=1e-5, *, fvec=None, rows_per_frame=1, xsum=No
     _call("b200svd_layernorm", _ptr(x), x.stride(0), _ptr(out), out.stride(0), rows, Cc, _ptr(gamma), _ptr(beta),
           float(eps), _ptr(fvec), fvec.stride(0) if fvec is not None else 0, rows_per_frame, _ptr(xsum),
           xsum.stride(0) if xsum is not None else 0, 1 if silu else 0, _stream(),
-          nbytes=2.0 * rows * Cc * (2 + (xsum is not None)))
+          nbytes=2.0 * rows * Cc * (2 + (xsum is not None)), desc=f"rows{rows} c{Cc}")
     return out
 
 
