@@ -98,6 +98,13 @@ int b200svd_small_attn(const void* q, int64_t ldq, const void* k, int64_t ldk, c
                        int64_t ldo, int b, int s_pixels, int heads, int lq, int lk, int kv_per_pixel, float scale,
                        void* stream);
 
+/* ---- per-pixel attention over frames on the tensor cores (tcgen05), head dim 64, K/V per pixel ------------
+ * Same contract as b200svd_small_attn with kv_per_pixel = 1: temporal self-attention (video_attention.py:145-148)
+ * and CAM cross-frame attention (cam/conditioning.py:65-68).  One CTA = 4 pixels x 1 head; frames are gathered by
+ * TMA through their row stride, scores are block-diagonal in a 128 x 128 tcgen05 tile. */
+int b200svd_pixel_attn(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o,
+                       int64_t ldo, int b, int s_pixels, int heads, int lq, int lk, float scale, void* stream);
+
 /* ---- GroupNorm(32) / LayerNorm, channel-last bf16, fp32 statistics ----------------------------------------
  * GroupNorm32 (diffusionmodules/util.py:274-276), Normalize (attention.py:132-135), CAM joint norm over
  * (C/32,F,H,W) (cam/conditioning.py:57-59: pass n = B, p = F*H*W), nn.LayerNorm (attention.py:528-530,

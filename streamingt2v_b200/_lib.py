@@ -88,6 +88,7 @@ PROTOTYPES = {
     "b200svd_gemm": [C.POINTER(GemmParams), _P],
     "b200svd_flash_attn": [_P, _I64, _P, _I64, _I, _I, _I, _F, _P],
     "b200svd_small_attn": [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _I, _I, _I, _I, _I, _I, _F, _P],
+    "b200svd_pixel_attn": [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _I, _I, _I, _I, _I, _F, _P],
     "b200svd_gn_stats": [_P, _I64, _I64, _I64, _I, _P, _P, _P, _P],
     "b200svd_gn_apply": [_P, _I64, _P, _I64, _I64, _I64, _I, _P, _P, _P, _F, _I, _P],
     "b200svd_layernorm": [_P, _I64, _P, _I64, _I64, _I, _P, _P, _F, _P, _I64, _I, _P, _I64, _I, _P],

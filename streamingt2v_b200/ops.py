@@ -266,7 +266,7 @@ def _conv_common(x, a_dims, a_strides, a_box, w, Cout, K, taps, m_ext, m_box, m_
 # ----------------------------------------------------------------------------------------------------------------
 # attention
 # ----------------------------------------------------------------------------------------------------------------
-_FAMILY = {"b200svd_flash_attn": "flash_attn", "b200svd_small_attn": "small_attn", "b200svd_gn_stats": "groupnorm",
+_FAMILY = {"b200svd_flash_attn": "flash_attn", "b200svd_small_attn": "small_attn", "b200svd_pixel_attn": "pixel_attn", "b200svd_gn_stats": "groupnorm",
            "b200svd_gn_apply": "groupnorm", "b200svd_layernorm": "layernorm"}
 
 
@@ -300,6 +300,13 @@ def small_attn(q, k, v, *, b, s, heads, lq, lk, kv_per_pixel=True, out=None):
     Cc = heads * 64
     if out is None:
         out = torch.empty((b * lq * s, Cc), dtype=torch.bfloat16, device=q.device)
+    if kv_per_pixel and all(t.data_ptr() % 16 == 0 for t in (q, k, v)):
+        # tensor-core path: 4 pixels x 32 padded frames per tcgen05 tile
+        _call("b200svd_pixel_attn", _ptr(q), q.stride(0), _ptr(k), k.stride(0), _ptr(v), v.stride(0), _ptr(out),
+              out.stride(0), b, s, heads, lq, lk, 64 ** -0.5, _stream(),
+              flops=4.0 * b * s * heads * lq * lk * 64, nbytes=2.0 * Cc * (2 * b * lq * s + 2 * b * lk * s),
+              desc=f"b{b} s{s} h{heads} {lq}x{lk}")
+        return out
     _call("b200svd_small_attn", _ptr(q), q.stride(0), _ptr(k), k.stride(0), _ptr(v), v.stride(0), _ptr(out),
           out.stride(0), b, s, heads, lq, lk, 1 if kv_per_pixel else 0, 64 ** -0.5, _stream(),
           flops=4.0 * b * s * heads * lq * lk * 64,
