@@ -6,8 +6,11 @@
 // (reference code/models/svd/sgm/modules/attention.py:320-351 SDPA / :427-446 xformers), batch = frames,
 // heads = C/64, sequence = H*W.
 //
-// CTA = TWO 128-row query tiles (A, B) of one (frame, head), ping-ponged so the tensor core works on one tile
-// while the other tile's softmax runs; K/V blocks are loaded once per CTA and shared by both tiles.
+// CTA = TWO 128-row query tiles (A, B) of one (frame, head); K/V blocks are loaded once per CTA and shared by both
+// tiles.  The (tile, key-block) work items t_k (k = 2*j + tile) rotate through THREE score buffers in TMEM, so the
+// QK^T MMA of item t_(k+3) is issued as soon as the PV MMA of t_k has been issued: a tile's next scores are ready
+// before its current softmax finishes (with one buffer per tile the softmax warps idled through their own
+// PV -> QK round trip and the MUFU pipe sat at 56%, profiles/r01_ncu_fa_v2_details.txt).
 //   warp 0      TMA producer (Q_A, Q_B once; K/V ring of 4 stages)
 //   warp 1      MMA issuer + TMEM owner
 //   warps 2..9  softmax: 4 warps per query tile, one query row per thread
@@ -36,7 +39,7 @@ constexpr int FA_KV_STAGES = 4;
 constexpr int FA_Q_BYTES = FA_BQ * FA_D * 2;        // 16 KB per query tile
 constexpr int FA_KV_TILE_BYTES = FA_BK * FA_D * 2;  // 16 KB each for K and V
 constexpr int FA_SMEM_BYTES = 2 * FA_Q_BYTES + FA_KV_STAGES * 2 * FA_KV_TILE_BYTES + 256;
-constexpr int FA_TMEM_COLS = 512;  // S_A [0,128) S_B [128,256) (P aliases the first 64 columns), O_A [256,320) O_B [320,384)
+constexpr int FA_TMEM_COLS = 512;  // score buffers [0,128) [128,256) [256,384) (P aliases the first 64 columns), O_A [384,448) O_B [448,512)
 constexpr int FA_THREADS = 10 * 32;
 constexpr float FA_RESCALE_THRESHOLD = 8.0f;  // log2 units
 
@@ -57,9 +60,9 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const FaParams p) {
   uint64_t* q_full = bars;
   uint64_t* kv_full = bars + 1;                       // [4]
   uint64_t* kv_empty = kv_full + FA_KV_STAGES;        // [4]
-  uint64_t* s_full = kv_empty + FA_KV_STAGES;         // [2]
-  uint64_t* p_full = s_full + 2;                      // [2]
-  uint64_t* pv_done = p_full + 2;                     // [2]
+  uint64_t* s_full = kv_empty + FA_KV_STAGES;         // [3] per score buffer
+  uint64_t* p_full = s_full + 3;                      // [3] per score buffer
+  uint64_t* pv_done = p_full + 3;                     // [2] per tile
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -74,11 +77,11 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const FaParams p) {
       mbar_init(&kv_full[s], 1);
       mbar_init(&kv_empty[s], 1);
     }
-    for (int x = 0; x < 2; ++x) {
-      mbar_init(&s_full[x], 1);
-      mbar_init(&p_full[x], 4);  // one arrive per softmax warp of the tile
-      mbar_init(&pv_done[x], 1);
+    for (int bf = 0; bf < 3; ++bf) {
+      mbar_init(&s_full[bf], 1);
+      mbar_init(&p_full[bf], 4);  // one arrive per softmax warp of the tile that owns the buffer this round
     }
+    for (int x = 0; x < 2; ++x) mbar_init(&pv_done[x], 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -113,46 +116,39 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const FaParams p) {
       constexpr uint32_t idesc_pv = make_idesc_f16(128, 64, 1, 0, 1);  // B (=V) is MN-major
       const uint64_t qdesc[2] = {smem_desc_k_sw128(smem_u32(sQ)), smem_desc_k_sw128(smem_u32(sQ + FA_Q_BYTES))};
       mbar_wait(q_full, 0);
-      mbar_wait(&kv_full[0], 0);
-      tc_fence_after();
-      {
-        const uint64_t kdesc = smem_desc_k_sw128(smem_u32(sKV));
-        for (int x = 0; x < 2; ++x) {
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk)
-            umma_f16_ss(tmem_base + x * 128, qdesc[x] + kk * 2, kdesc + kk * 2, idesc_qk, kk > 0);
-          umma_commit(&s_full[x]);
-        }
-      }
-      for (int j = 0; j < nkb; ++j) {
-        const int st = j % FA_KV_STAGES;
-        const uint64_t vdesc = smem_desc_mn_sw128(smem_u32(sKV + st * 2 * FA_KV_TILE_BYTES + FA_KV_TILE_BYTES));
-        for (int x = 0; x < 2; ++x) {
-          // P_x(j) is in TMEM (and S_x(j) fully consumed)
-          mbar_wait(&p_full[x], j & 1);
+      const int nitems = 2 * nkb;  // work items t_k: key block j = k/2, tile x = k%2, score buffer k%3
+      int kv_ready = -1;           // highest key block whose K/V stage has been waited for
+      auto issue_qk = [&](int k) {
+        const int j = k >> 1, x = k & 1, bf = k % 3;
+        if (j > kv_ready) {
+          mbar_wait(&kv_full[j % FA_KV_STAGES], (j / FA_KV_STAGES) & 1);
           tc_fence_after();
-#pragma unroll
-          for (int kk = 0; kk < 8; ++kk) {
-            // A = P from TMEM: 16 bf16 of K per MMA = 8 packed 32-bit columns; V: +2048 B (= +128 in addr>>4) per 16 keys
-            umma_f16_ts(tmem_base + 256 + x * 64, tmem_base + x * 128 + kk * 8, vdesc + (uint64_t)(kk * 128), idesc_pv,
-                        (j > 0 || kk > 0) ? 1u : 0u);
-          }
-          umma_commit(&pv_done[x]);
-          if (x == 1) umma_commit(&kv_empty[st]);
-          if (j + 1 < nkb) {
-            const int s1 = (j + 1) % FA_KV_STAGES;
-            if (x == 0) {
-              mbar_wait(&kv_full[s1], ((j + 1) / FA_KV_STAGES) & 1);
-              tc_fence_after();
-            }
-            const uint64_t kdesc = smem_desc_k_sw128(smem_u32(sKV + s1 * 2 * FA_KV_TILE_BYTES));
-            // executes after PV_x(j) in the tensor pipe (issue order), which was the last reader of P_x(j)
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk)
-              umma_f16_ss(tmem_base + x * 128, qdesc[x] + kk * 2, kdesc + kk * 2, idesc_qk, kk > 0);
-            umma_commit(&s_full[x]);
-          }
+          kv_ready = j;
         }
+        const uint64_t kdesc = smem_desc_k_sw128(smem_u32(sKV + (j % FA_KV_STAGES) * 2 * FA_KV_TILE_BYTES));
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          umma_f16_ss(tmem_base + bf * 128, qdesc[x] + kk * 2, kdesc + kk * 2, idesc_qk, kk > 0);
+        umma_commit(&s_full[bf]);
+      };
+      for (int k = 0; k < 3 && k < nitems; ++k) issue_qk(k);
+      for (int k = 0; k < nitems; ++k) {
+        const int j = k >> 1, x = k & 1, bf = k % 3;
+        const int st = j % FA_KV_STAGES;
+        // P(t_k) is in TMEM (and the scores of t_k fully consumed)
+        mbar_wait(&p_full[bf], (k / 3) & 1);
+        tc_fence_after();
+        const uint64_t vdesc = smem_desc_mn_sw128(smem_u32(sKV + st * 2 * FA_KV_TILE_BYTES + FA_KV_TILE_BYTES));
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          // A = P from TMEM: 16 bf16 of K per MMA = 8 packed 32-bit columns; V: +2048 B (= +128 in addr>>4) per 16 keys
+          umma_f16_ts(tmem_base + 384 + x * 64, tmem_base + bf * 128 + kk * 8, vdesc + (uint64_t)(kk * 128), idesc_pv,
+                      (j > 0 || kk > 0) ? 1u : 0u);
+        }
+        umma_commit(&pv_done[x]);
+        if (x == 1) umma_commit(&kv_empty[st]);  // both tiles' QK and PV of key block j have been issued
+        // the buffer of t_k is free again once PV(t_k) has executed (tensor pipe runs in issue order)
+        if (k + 3 < nitems) issue_qk(k + 3);
       }
     }
     __syncwarp();
@@ -162,13 +158,14 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const FaParams p) {
     const int qd = warp & 3;
     const int r = qd * 32 + lane;  // query row in tile == TMEM lane
     const uint32_t tl = ((uint32_t)(qd * 32)) << 16;
-    const uint32_t tS = tmem_base + x * 128 + tl;
-    const uint32_t tO = tmem_base + 256 + x * 64 + tl;
+    const uint32_t tO = tmem_base + 384 + x * 64 + tl;
     float m_used = -INFINITY, l_run = 0.f;
     const float c = p.scale_log2;
 
     for (int j = 0; j < nkb; ++j) {
-      mbar_wait(&s_full[x], j & 1);
+      const int k = 2 * j + x, bf = k % 3;
+      const uint32_t tS = tmem_base + bf * 128 + tl;
+      mbar_wait(&s_full[bf], (k / 3) & 1);
       tc_fence_after();
       // pass 1 over the row (TMEM reads are cheap; keeping all 128 scores live would exceed the 168-register
       // budget that 10 warps per CTA leave per thread): block max
@@ -255,7 +252,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const FaParams p) {
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[x]);
+      if (lane == 0) mbar_arrive(&p_full[bf]);
     }
     // epilogue: O / l -> bf16 -> 128 B contiguous per row
     mbar_wait(&pv_done[x], (nkb - 1) & 1);
