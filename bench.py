@@ -287,6 +287,14 @@ def run_ours(args):
                 "launches": g["launches"], "avg_launch_ms": g["ms"] / g["launches"],
                 "share_of_step": g["ms"] / sum(v["ms"] for v in prof.families.values()),
                 "traffic": None, "traffic_note": "see profiles/ for the ncu --set full capture of this kernel"}
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))["mtgemm_conv3x3_L0_320to320"]
+            roof["traffic"] = tr["traffic_bytes"]
+            roof["traffic_note"] = (f"ncu --set full, one launch of the dominant conv shape ({tr['launch']}): "
+                                    f"{tr['traffic_bytes'] / 1e6:.0f} MB DRAM vs {tr['algorithmic_bytes'] / 1e6:.0f} MB "
+                                    f"algorithmic; roofline.achieved aggregates all {g['launches']} launches of the step")
+        except Exception:
+            pass
 
     if rank == 0:
         sps = dist_utils.aggregate_throughput(args.steps, world, ms)
