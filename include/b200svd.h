@@ -140,6 +140,10 @@ int b200svd_add_silu(const float* a, const float* b, void* out, int64_t total, i
 int b200svd_copy2d(const void* src, int64_t lds, void* dst, int64_t ldd, int64_t rows, int cols, void* stream);
 int b200svd_add_rows(void* dst, int64_t ldd, const void* src, int64_t lds, int64_t rows, int64_t src_rows, int cols,
                      void* stream);
+/* VAE decoder AttnBlock (diffusionmodules/model.py:180-195, one head of width C): row softmax of fp32 scores to
+ * bf16 probabilities, and a bf16 transpose that turns V into the K-major operand of the P.V GEMM. */
+int b200svd_softmax_rows(const float* in, int64_t lds, void* out, int64_t ldo, int64_t rows, int cols, void* stream);
+int b200svd_transpose(const void* in, int64_t ldi, void* out, int64_t ldo, int rows, int cols, void* stream);
 int b200svd_apm_mix(const float* ctx, int n, int l, int d, const float* w, const float* wb, const float* ln_g,
                     const float* ln_b, const float* alpha, void* out, void* stream);
 

@@ -99,6 +99,8 @@ PROTOTYPES = {
     "b200svd_add_silu": [_P, _P, _P, _I64, _I, _P],
     "b200svd_copy2d": [_P, _I64, _P, _I64, _I64, _I, _P],
     "b200svd_add_rows": [_P, _I64, _P, _I64, _I64, _I64, _I, _P],
+    "b200svd_softmax_rows": [_P, _I64, _P, _I64, _I64, _I, _P],
+    "b200svd_transpose": [_P, _I64, _P, _I64, _I, _I, _P],
     "b200svd_apm_mix": [_P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P],
 }
 

@@ -363,3 +363,70 @@ def synth_state_dict_fast(shapes: Dict[str, tuple], seed: int = 0):
             v = torch.randn(shape, generator=g) * (fan_in ** -0.5)
         sd[name] = v
     return sd
+
+
+# --------------------------------------------------------------------------------------------------------------
+# temporal VAE decoder (AutoencodingEngine.decode -> VideoDecoder; reference
+# code/models/svd/sgm/modules/autoencoding/temporal_ae.py:291-347, diffusionmodules/model.py:604-748)
+# --------------------------------------------------------------------------------------------------------------
+@dataclass(frozen=True)
+class VaeConfig:
+    """Defaults = decoder_config of the shipped checkpoint (reference code/config.yaml:242-257)."""
+    ch: int = 128
+    ch_mult: Tuple[int, ...] = (1, 2, 4, 4)
+    num_res_blocks: int = 2
+    z_channels: int = 4
+    out_ch: int = 3
+
+
+def vae_decoder_plan(cfg: VaeConfig):
+    """[(kind, prefix, cin, cout)] in execution order (Decoder.forward, model.py:715-748)."""
+    plan = []
+    block_in = cfg.ch * cfg.ch_mult[-1]
+    plan.append(("conv_in", "conv_in", cfg.z_channels, block_in))
+    plan.append(("res", "mid.block_1", block_in, block_in))
+    plan.append(("attn", "mid.attn_1", block_in, block_in))
+    plan.append(("res", "mid.block_2", block_in, block_in))
+    for i_level in reversed(range(len(cfg.ch_mult))):
+        block_out = cfg.ch * cfg.ch_mult[i_level]
+        for i_block in range(cfg.num_res_blocks + 1):
+            plan.append(("res", f"up.{i_level}.block.{i_block}", block_in, block_out))
+            block_in = block_out
+        if i_level != 0:
+            plan.append(("up", f"up.{i_level}.upsample", block_in, block_in))
+    plan.append(("out", "", block_in, cfg.out_ch))
+    return plan
+
+
+def vae_decoder_param_shapes(cfg: VaeConfig) -> Dict[str, tuple]:
+    d: Dict[str, tuple] = {}
+    for kind, p, cin, cout in vae_decoder_plan(cfg):
+        if kind == "conv_in":
+            _conv(d, p, cin, cout)
+        elif kind == "res":
+            _norm(d, p + ".norm1", cin)
+            _conv(d, p + ".conv1", cin, cout)
+            _norm(d, p + ".norm2", cout)
+            _conv(d, p + ".conv2", cout, cout)
+            if cin != cout:
+                _conv(d, p + ".nin_shortcut", cin, cout, 1)
+            t = p + ".time_stack"
+            _norm(d, t + ".in_layers.0", cout)
+            d[t + ".in_layers.2.weight"] = (cout, cout, 3, 1, 1)
+            d[t + ".in_layers.2.bias"] = (cout,)
+            _norm(d, t + ".out_layers.0", cout)
+            d[t + ".out_layers.3.weight"] = (cout, cout, 3, 1, 1)
+            d[t + ".out_layers.3.bias"] = (cout,)
+            d[p + ".mix_factor"] = (1,)
+        elif kind == "attn":
+            _norm(d, p + ".norm", cin)
+            for n in ("q", "k", "v", "proj_out"):
+                _conv(d, f"{p}.{n}", cin, cin, 1)
+        elif kind == "up":
+            _conv(d, p + ".conv", cin, cin)
+        elif kind == "out":
+            _norm(d, "norm_out", cin)
+            _conv(d, "conv_out", cin, cout)
+            d["conv_out.time_mix_conv.weight"] = (cout, cout, 3, 1, 1)
+            d["conv_out.time_mix_conv.bias"] = (cout,)
+    return d

@@ -260,3 +260,89 @@ int b200svd_apm_mix(const float* ctx, int n, int l, int d, const float* w, const
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------------------------
+// Single-head attention helpers for the VAE decoder's AttnBlock (reference diffusionmodules/model.py:180-195):
+// row softmax of fp32 scores -> bf16 probabilities, and a bf16 matrix transpose (V^T as the K-major GEMM operand).
+// ------------------------------------------------------------------------------------------------------------------
+namespace b200 {
+
+// one block per row; in: fp32 [rows][lds] (already scaled), out: bf16 [rows][ldo]; cols % 4 == 0
+__global__ void softmax_rows_kernel(const float* __restrict__ in, int64_t lds, __nv_bfloat16* __restrict__ out,
+                                    int64_t ldo, int cols) {
+  __shared__ float red[32];
+  const int64_t row = blockIdx.x;
+  const float4* src = reinterpret_cast<const float4*>(in + row * lds);
+  const int nv = cols >> 2;
+  float mx = -INFINITY;
+  for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+    const float4 v = __ldg(src + i);
+    mx = fmaxf(mx, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+  }
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = red[0];
+  for (int i = 1; i < (int)(blockDim.x >> 5); ++i) mx = fmaxf(mx, red[i]);
+  __syncthreads();
+  float sum = 0.f;
+  for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+    const float4 v = __ldg(src + i);
+    sum += __expf(v.x - mx) + __expf(v.y - mx) + __expf(v.z - mx) + __expf(v.w - mx);
+  }
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  float tot = 0.f;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) tot += red[i];
+  const float inv = 1.0f / tot;
+  uint2* dst = reinterpret_cast<uint2*>(out + row * ldo);
+  for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+    const float4 v = __ldg(src + i);
+    dst[i] = make_uint2(pack_bf16x2(__expf(v.x - mx) * inv, __expf(v.y - mx) * inv),
+                        pack_bf16x2(__expf(v.z - mx) * inv, __expf(v.w - mx) * inv));
+  }
+}
+
+// out[c][r] = in[r][c]; 32 x 32 tiles through shared memory
+__global__ void transpose_kernel(const __nv_bfloat16* __restrict__ in, int64_t ldi, __nv_bfloat16* __restrict__ out,
+                                 int64_t ldo, int rows, int cols) {
+  __shared__ __nv_bfloat16 tile[32][34];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    if (r < rows && c < cols) tile[i][threadIdx.x] = in[(int64_t)r * ldi + c];
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (r < rows && c < cols) out[(int64_t)c * ldo + r] = tile[threadIdx.x][i];
+  }
+}
+
+}  // namespace b200
+
+extern "C" {
+
+int b200svd_softmax_rows(const float* in, int64_t lds, void* out, int64_t ldo, int64_t rows, int cols, void* stream) {
+  using namespace b200;
+  if (cols % 4 || lds % 4 || ldo % 4) {
+    set_error("softmax_rows: cols and leading dims must be multiples of 4");
+    return 1;
+  }
+  softmax_rows_kernel<<<(unsigned)rows, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      in, lds, reinterpret_cast<__nv_bfloat16*>(out), ldo, cols);
+  B200_CHECK_LAUNCH("softmax_rows");
+  return 0;
+}
+
+int b200svd_transpose(const void* in, int64_t ldi, void* out, int64_t ldo, int rows, int cols, void* stream) {
+  using namespace b200;
+  dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
+  transpose_kernel<<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(in), ldi, reinterpret_cast<__nv_bfloat16*>(out), ldo, rows, cols);
+  B200_CHECK_LAUNCH("transpose");
+  return 0;
+}
+
+}  // extern "C"

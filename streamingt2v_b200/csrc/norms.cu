@@ -92,12 +92,25 @@ __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx
     if (is_last) counters[n] = 0;  // self-reset for the next launch
   }
   __syncthreads();
-  if (is_last && threadIdx.x < 64) {
+  if (is_last) {
+    // fixed-order final reduction over the chunk partials, spread over the whole block: thread t owns pair t%64 and
+    // the chunks congruent to t/64 modulo (blockDim/64); the (blockDim/64) strided sums are then added in order
     __threadfence();
-    const int g = threadIdx.x & 31, which = threadIdx.x >> 5;
-    double a = 0.0;
-    for (int c = 0; c < chunks; ++c) a += partial[(((int64_t)n * chunks + c) * 32 + g) * 2 + which];
-    sums[((int64_t)n * 32 + g) * 2 + which] = a;
+    const int pairs = 64;
+    const int parts = blockDim.x / pairs;  // >= 2 (blockDim >= 160)
+    double* dsm = reinterpret_cast<double*>(sm);  // reuse the staging area: needs parts*64 doubles <= 2*C*rstep floats
+    const int pr = threadIdx.x % pairs, part = threadIdx.x / pairs;
+    if (part < parts) {
+      double a = 0.0;
+      for (int c = part; c < chunks; c += parts) a += partial[((int64_t)n * chunks + c) * 64 + (pr & 31) * 2 + (pr >> 5)];
+      dsm[part * pairs + pr] = a;
+    }
+    __syncthreads();
+    if (threadIdx.x < pairs) {
+      double a = 0.0;
+      for (int q = 0; q < parts; ++q) a += dsm[q * pairs + threadIdx.x];
+      sums[((int64_t)n * 32 + (threadIdx.x & 31)) * 2 + (threadIdx.x >> 5)] = a;
+    }
   }
 }
 
@@ -346,7 +359,9 @@ static int gn_geometry(int C, int64_t n, int P, int* threads, int* rows_per_chun
   int64_t rpc = ((int64_t)P * n + target_ctas - 1) / target_ctas;
   rpc = ((rpc + min_rpc - 1) / min_rpc) * min_rpc;
   if (rpc < min_rpc) rpc = min_rpc;
-  if (rpc > 256) rpc = 256 / min_rpc * min_rpc > 0 ? 256 / min_rpc * min_rpc : min_rpc;
+  int64_t cap = 256;
+  while ((int64_t)P / cap > 2048 && cap < 4096) cap *= 2;  // bound the number of chunk partials per sample
+  if (rpc > cap) rpc = cap / min_rpc * min_rpc > 0 ? cap / min_rpc * min_rpc : min_rpc;
   if (rpc > P) rpc = P;
   *rows_per_chunk = (int)rpc;
   *chunks = (int)((P + rpc - 1) / rpc);

@@ -427,3 +427,38 @@ def apm_mix(ctx, w, wb, ln_g, ln_b, alpha):
     _call("b200svd_apm_mix", _ptr(ctx), N, L, D, _ptr(w), _ptr(wb), _ptr(ln_g), _ptr(ln_b), _ptr(alpha), _ptr(out),
           _stream())
     return out
+
+
+def softmax_rows(scores, out=None):
+    """scores: fp32 [rows, cols] (already scaled) -> bf16 probabilities."""
+    assert scores.dtype == torch.float32 and scores.dim() == 2 and scores.stride(1) == 1
+    rows, cols = scores.shape
+    if out is None:
+        out = torch.empty((rows, cols), dtype=torch.bfloat16, device=scores.device)
+    _call("b200svd_softmax_rows", _ptr(scores), scores.stride(0), _ptr(out), out.stride(0), rows, cols, _stream(),
+          nbytes=6.0 * rows * cols)
+    return out
+
+
+def transpose(x):
+    """bf16 [R, C] -> contiguous [C, R]."""
+    assert x.dtype == torch.bfloat16 and x.dim() == 2 and x.stride(1) == 1
+    R, Cc = x.shape
+    out = torch.empty((Cc, R), dtype=torch.bfloat16, device=x.device)
+    _call("b200svd_transpose", _ptr(x), x.stride(0), _ptr(out), out.stride(0), R, Cc, _stream(), nbytes=4.0 * R * Cc)
+    return out
+
+
+def attention_single_head(q, k, v, n, s):
+    """softmax(q k^T / sqrt(C)) v per frame, one head of width C (VAE AttnBlock).  q, k, v: contiguous [(n s), C] bf16.
+    Built from the tensor-core GEMM (scores in fp32), a row-softmax kernel and a transpose."""
+    Cc = q.shape[1]
+    out = torch.empty((n * s, Cc), dtype=torch.bfloat16, device=q.device)
+    scale = float(Cc) ** -0.5
+    for f in range(n):
+        sl = slice(f * s, (f + 1) * s)
+        scores = linear(q[sl], k[sl][None], None, out_fp32=True, s_acc=scale)          # [s, s] fp32
+        probs = softmax_rows(scores)
+        vt = transpose(v[sl])                                                           # [C, s]
+        linear(probs, vt[None], None, out=out[sl])
+    return out

@@ -131,7 +131,7 @@ def group_norm(x, n, p, gamma, beta, eps, *, silu=False, out=None, sums=None):
     y = F.group_norm(x.float().reshape(n, p, c).permute(0, 2, 1), 32, gamma, beta, eps)
     if silu:
         y = F.silu(y)
-    y = y.permute(0, 2, 1).reshape(n * p, c).to(torch.bfloat16)
+    y = y.permute(0, 2, 1).reshape(n * p, c).to(torch.bfloat16).contiguous()
     if out is not None:
         out.copy_(y)
         return out
@@ -209,3 +209,30 @@ def apm_mix(ctx, w, wb, ln_g, ln_b, alpha):
     mixed = F.conv1d(ctx, w.reshape(1, L, 3), wb, padding=1)
     mixed = F.layer_norm(mixed, (D,), ln_g, ln_b, 1e-5)
     return (ctx[:, :1] + mixed * F.silu(alpha))[:, 0].to(torch.bfloat16)
+
+
+def softmax_rows(scores, out=None):
+    _count()
+    p = torch.softmax(scores.float(), dim=-1).to(torch.bfloat16)
+    if out is not None:
+        out.copy_(p)
+        return out
+    return p
+
+
+def transpose(x):
+    _count()
+    return x.t().contiguous()
+
+
+def attention_single_head(q, k, v, n, s):
+    Cc = q.shape[1]
+    out = torch.empty((n * s, Cc), dtype=torch.bfloat16)
+    scale = float(Cc) ** -0.5
+    for f in range(n):
+        sl = slice(f * s, (f + 1) * s)
+        scores = linear(q[sl], k[sl][None], None, out_fp32=True, s_acc=scale)
+        probs = softmax_rows(scores)
+        vt = transpose(v[sl])
+        linear(probs, vt[None], None, out=out[sl])
+    return out
