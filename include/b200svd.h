@@ -77,10 +77,16 @@ typedef struct {
   const void* res2;
   int64_t ld2;
   float s2;
-  int32_t bn; /* N tile: 32, 64, 128 or 160 (0 = choose) */
+  int32_t bn; /* N tile: 32, 64, 128, 160 or 256 (0 = choose) */
 } b200svd_gemm_params;
 
 int b200svd_gemm(const b200svd_gemm_params* p, void* stream);
+
+/* Tuning knob (no reference counterpart): when the 160/256-wide tiles run as 2-SM (tcgen05 cta_group::2, CTA-pair)
+ * tiles.  0 = never, 2 = automatic (the default: every launch with at least two M tiles; also settable through the
+ * environment variable B200SVD_PAIR), 1 = as 2 plus the 128-wide tile.  Other values only query.  Returns the
+ * previous mode. */
+int b200svd_gemm_pair_mode(int mode);
 
 /* ---- FlashAttention forward, head dim 64 (tcgen05 + TMEM + TMA) -------------------------------------------
  * Spatial self-attention core of BasicTransformerBlock.attn1 (attention.py:320-351 SDPA / :427-446 xformers).

@@ -76,6 +76,8 @@ def load():
     lib.b200svd_init.restype = C.c_int
     lib.b200svd_init.argtypes = [C.c_int]
     _declare(lib)
+    lib.b200svd_gemm_pair_mode.restype = C.c_int
+    lib.b200svd_gemm_pair_mode.argtypes = [C.c_int]
     lib.b200svd_gn_scratch_doubles.restype = C.c_int64
     lib.b200svd_gn_scratch_doubles.argtypes = [C.c_int64, C.c_int64, C.c_int]
     _LIB = lib

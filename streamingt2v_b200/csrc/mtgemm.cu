@@ -22,6 +22,7 @@
 // 256-wide tile for the latter.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/b200svd.h"
@@ -69,24 +70,35 @@ constexpr int RES_BUFS = 3;
 constexpr int RES_BUF_BYTES = 128 * 64 * 2;  // one 128-row x 64-column bf16 sub-tile
 constexpr int OUT_BUF_BYTES = 32 * 64 * 2;   // one quadrant (32 rows) x 64 columns
 
-template <int BN>
+template <int BN, bool PAIR>
 struct TileCfg {
-  static constexpr int B_STAGE_BYTES = BN * BK * 2;
+  // PAIR: two CTAs of a cluster compute a 256 x BN tile with one cta_group::2 MMA stream; each CTA stages its own
+  // 128 A rows and HALF of the B tile (the tensor cores of the pair share B), which halves B traffic per FLOP.
+  static constexpr int B_ROWS = PAIR ? BN / 2 : BN;
+  static constexpr int B_STAGE_BYTES = B_ROWS * BK * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STAGES = (BN >= 256) ? 3 : (BN >= 128) ? 4 : 6;
   static constexpr int ACC_STRIDE = (BN <= 32) ? 32 : (BN <= 64) ? 64 : (BN <= 128) ? 128 : 256;
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
   static constexpr int NSUB = (BN + 63) / 64;
-  static constexpr int OUT_BYTES = 4 * 2 * OUT_BUF_BYTES;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + RES_BUFS * RES_BUF_BYTES + OUT_BYTES + 512;
+  // staging buffers per quadrant: 3 lets the TMA store of sub-tile i drain while sub-tile i+1 is being written
+  // (bulk wait_group.read 1); the single-CTA 256-wide tile only has room for 2 (wait_group.read 0)
+  static constexpr int OUT_BUFS = (BN >= 256 && !PAIR) ? 2 : 3;
+  static constexpr int OUT_BYTES = 4 * OUT_BUFS * OUT_BUF_BYTES;
+  static constexpr int FIXED_BYTES = RES_BUFS * RES_BUF_BYTES + OUT_BYTES + 512;
+  static constexpr int STAGES_FIT = (232448 - FIXED_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_FIT > 6 ? 6 : STAGES_FIT;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + FIXED_BYTES;
+  static_assert(STAGES >= 3, "pipeline depth");
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
   static_assert(STAGE_BYTES % 1024 == 0, "stage alignment");
 };
 
-__device__ __forceinline__ void decode_tile(const GemmDev& p, uint32_t tile, uint32_t& n_tile, uint32_t& mb1,
-                                            uint32_t& mb2, uint32_t& mb3) {
+// `tile` enumerates (N tile fastest, then M tile) — in PAIR mode (M-tile PAIR); mrank selects this CTA's M tile of the
+// pair.  An M tile index past the end decodes to coordinates beyond the extents (all rows out of bounds).
+__device__ __forceinline__ void decode_tile(const GemmDev& p, uint32_t tile, uint32_t mmul, uint32_t mrank,
+                                            uint32_t& n_tile, uint32_t& mb1, uint32_t& mb2, uint32_t& mb3) {
   n_tile = tile % p.n_tiles;
-  uint32_t mt = tile / p.n_tiles;
+  uint32_t mt = (tile / p.n_tiles) * mmul + mrank;
   const uint32_t t1 = mt % p.m_tiles[0];
   mt /= p.m_tiles[0];
   const uint32_t t2 = mt % p.m_tiles[1];
@@ -96,12 +108,12 @@ __device__ __forceinline__ void decode_tile(const GemmDev& p, uint32_t tile, uin
   mb3 = t3 << p.m_lb[2];
 }
 
-template <int BN>
+template <int BN, bool PAIR>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 mtgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
               const __grid_constant__ CUtensorMap tmO64, const __grid_constant__ CUtensorMap tmO32,
               const __grid_constant__ CUtensorMap tmR64, const __grid_constant__ CUtensorMap tmR32, const GemmDev p) {
-  using Cfg = TileCfg<BN>;
+  using Cfg = TileCfg<BN, PAIR>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ __align__(1024) uint8_t smem[];  // SWIZZLE_128B operands need 1024-byte alignment
   if ((smem_u32(smem) & 1023u) != 0) __trap();
@@ -118,7 +130,8 @@ mtgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  const uint32_t tile_begin = blockIdx.x * p.tiles_per_cta;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;  // 0 = leader CTA of the pair (issues the MMAs)
+  const uint32_t tile_begin = (PAIR ? (blockIdx.x >> 1) : blockIdx.x) * p.tiles_per_cta;
   const uint32_t tile_end = min(tile_begin + p.tiles_per_cta, p.total_tiles);
   const bool geglu = (p.act == B200SVD_ACT_GEGLU);
   const uint32_t n_out = geglu ? p.n / 2 : p.n;
@@ -139,7 +152,7 @@ mtgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&acc_full[b], 1);
-      mbar_init(&acc_empty[b], EPI_WARPS);  // one arrive per epilogue warp
+      mbar_init(&acc_empty[b], PAIR ? 2 * EPI_WARPS : EPI_WARPS);  // one arrive per epilogue warp (of both CTAs)
     }
     for (int b = 0; b < RES_BUFS; ++b) {
       mbar_init(&res_full[b], 1);
@@ -148,11 +161,17 @@ mtgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-    tmem_relinquish();
+    if (PAIR) {
+      tmem_alloc_2sm(tmem_slot, Cfg::TMEM_COLS);
+      tmem_relinquish_2sm();
+    } else {
+      tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();  // peer barriers are initialised before any remote arrive / multicast commit
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t iters_per_tile = p.taps * p.kblocks;
@@ -163,7 +182,7 @@ mtgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       uint32_t it = 0;
       for (uint32_t tile = tile_begin; tile < tile_end; ++tile) {
         uint32_t n_tile, mb1, mb2, mb3;
-        decode_tile(p, tile, n_tile, mb1, mb2, mb3);
+        decode_tile(p, tile, PAIR ? 2u : 1u, rank, n_tile, mb1, mb2, mb3);
         int base[5] = {0, 0, 0, 0, 0};
         base[p.m_adim[0]] += (int)mb1;
         base[p.m_adim[1]] += (int)mb2;
@@ -180,17 +199,25 @@ mtgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             const uint32_t ph = (it / STAGES) & 1;
             mbar_wait(&empty_bar[s], ph ^ 1);
             uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
-            mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
-            tma_load_5d(sa, &tmA, &full_bar[s], c0 + (int)(kb * BK), c1, c2, c3, c4);
-            tma_load_3d(sa + A_STAGE_BYTES, &tmB, &full_bar[s], (int)(kb * BK), n0, (int)tap);
+            if (PAIR) {
+              // both CTAs' loads are credited to the leader's barrier; the leader expects the bytes of the pair
+              if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * Cfg::STAGE_BYTES);
+              tma_load_5d_2sm(sa, &tmA, &full_bar[s], c0 + (int)(kb * BK), c1, c2, c3, c4);
+              tma_load_3d_2sm(sa + A_STAGE_BYTES, &tmB, &full_bar[s], (int)(kb * BK), n0 + (int)(rank * (BN / 2)),
+                              (int)tap);
+            } else {
+              mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+              tma_load_5d(sa, &tmA, &full_bar[s], c0 + (int)(kb * BK), c1, c2, c3, c4);
+              tma_load_3d(sa + A_STAGE_BYTES, &tmB, &full_bar[s], (int)(kb * BK), n0, (int)tap);
+            }
           }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===================== MMA issuer =====================
-      constexpr uint32_t idesc = make_idesc_f16(BM, BN, /*bf16*/ 1, 0, 0);
+    if (lane == 0 && rank == 0) {
+      // ===================== MMA issuer (leader CTA only in PAIR mode) =====================
+      constexpr uint32_t idesc = make_idesc_f16(PAIR ? 2 * BM : BM, BN, /*bf16*/ 1, 0, 0);
       uint32_t it = 0, tcount = 0;
       for (uint32_t tile = tile_begin; tile < tile_end; ++tile, ++tcount) {
         const uint32_t b = tcount & 1;
@@ -208,11 +235,18 @@ mtgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 #pragma unroll
           for (int kk = 0; kk < BK / 16; ++kk) {
             // advance 16 elements (32 B) along K inside the 128B swizzle atom: +2 in the (addr>>4) field
-            umma_f16_ss(tacc, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, (i > 0 || kk > 0) ? 1u : 0u);
+            if (PAIR)
+              umma_f16_ss_2sm(tacc, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, (i > 0 || kk > 0) ? 1u : 0u);
+            else
+              umma_f16_ss(tacc, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, (i > 0 || kk > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs have read it
+          // frees the smem stage (in both CTAs of a pair) once these MMAs have read it
+          if (PAIR) umma_commit_2sm(&empty_bar[s]);
+          else umma_commit(&empty_bar[s]);
         }
-        umma_commit(&acc_full[b]);  // accumulator complete
+        // accumulator complete (signalled to the epilogue warps of both CTAs of a pair)
+        if (PAIR) umma_commit_2sm(&acc_full[b]);
+        else umma_commit(&acc_full[b]);
       }
     }
     __syncwarp();
@@ -222,7 +256,7 @@ mtgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       uint32_t rcount = 0;
       for (uint32_t tile = tile_begin; tile < tile_end; ++tile) {
         uint32_t n_tile, mb1, mb2, mb3;
-        decode_tile(p, tile, n_tile, mb1, mb2, mb3);
+        decode_tile(p, tile, PAIR ? 2u : 1u, rank, n_tile, mb1, mb2, mb3);
         const uint32_t otile0 = n_tile * tile_out_w;
         for (uint32_t s = 0; s < nsub_out; ++s) {
           const uint32_t ocol0 = otile0 + 64 * s;
@@ -249,14 +283,14 @@ mtgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     const uint32_t qo1 = qoff & ((1u << lb1) - 1);
     const uint32_t qo2 = (qoff >> lb1) & ((1u << lb2) - 1);
     const uint32_t qo3 = qoff >> (lb1 + lb2);
-    uint8_t* outq = out_base + q * 2 * OUT_BUF_BYTES;
+    uint8_t* outq = out_base + q * Cfg::OUT_BUFS * OUT_BUF_BYTES;
     const bool bias_vec = p.bias != nullptr && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0;
     const bool fvec_vec = p.fvec != nullptr && (reinterpret_cast<uintptr_t>(p.fvec) & 15) == 0 && (p.ldf & 3) == 0;
 
     uint32_t tcount = 0, ocount = 0, rcount = 0;
     for (uint32_t tile = tile_begin; tile < tile_end; ++tile, ++tcount) {
       uint32_t n_tile, mb1, mb2, mb3;
-      decode_tile(p, tile, n_tile, mb1, mb2, mb3);
+      decode_tile(p, tile, PAIR ? 2u : 1u, rank, n_tile, mb1, mb2, mb3);
       const uint32_t n0 = n_tile * BN;
       const uint32_t otile0 = n_tile * tile_out_w;
       const uint32_t m1 = mb1 + (r & ((1u << lb1) - 1));
@@ -344,7 +378,7 @@ mtgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             rb = rcount % RES_BUFS;
             mbar_wait(&res_full[rb], (rcount / RES_BUFS) & 1);
           }
-          uint8_t* ob = outq + (ocount & 1) * OUT_BUF_BYTES;
+          uint8_t* ob = outq + (ocount % Cfg::OUT_BUFS) * OUT_BUF_BYTES;
           if ((uint32_t)(16 * g) < subw) {
             const uint32_t acol = 64 * s + 16 * g;  // accumulator column (value half for GEGLU)
             uint32_t va[16], vg[16];
@@ -420,14 +454,19 @@ mtgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             // last TMEM read of this tile is done: hand the accumulator buffer back before the store
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[b]);
+            if (lane == 0) {
+              if (PAIR) mbar_arrive_leader(&acc_empty[b]);
+              else mbar_arrive(&acc_empty[b]);
+            }
           }
           named_bar_sync(1 + q, 128);  // the quadrant's 32 x subw block is complete in staging
           if (g == 0 && lane == 0) {
             tma_store_5d(subw == 64 ? &tmO64 : &tmO32, ob, (int)ocol0, (int)(mb1 + qo1), (int)(mb2 + qo2),
                          (int)(mb3 + qo3), 0);
             tma_store_commit();
-            tma_store_wait_read0();  // staging buffer may be overwritten two sub-tiles from now
+            // all but the newest OUT_BUFS-2 stores have finished reading: the buffer written next-but-one is free
+            // by the time its writers pass the next named barrier
+            tma_store_wait_read<Cfg::OUT_BUFS - 2>();
           }
           ++ocount;
         }
@@ -468,17 +507,22 @@ mtgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&acc_empty[b]);
+        if (lane == 0) {
+          if (PAIR) mbar_arrive_leader(&acc_empty[b]);
+          else mbar_arrive(&acc_empty[b]);
+        }
       }
     }
     if (p.tma_epi && g == 0 && lane == 0) tma_store_wait_all();  // all bulk stores of this thread have landed
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();  // the peer may still be reading its accumulators / smem stages
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if (PAIR) tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS);
+    else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
@@ -509,14 +553,14 @@ static int encode_rows_view(CUtensorMap* tm, const void* base, int64_t ld, uint3
   return box_cols == 64 ? encode_tmap_bf16(tm, base, 5, dims, str, box) : encode_tmap_bf16_sw64(tm, base, 5, dims, str, box);
 }
 
-template <int BN>
+template <int BN, bool PAIR>
 static int launch(const b200svd_gemm_params* p, const CUtensorMap& tmA, const GemmDev& d, cudaStream_t st) {
-  using Cfg = TileCfg<BN>;
-  // weights [taps][n][k] -> TMA dims (k, n, taps)
+  using Cfg = TileCfg<BN, PAIR>;
+  // weights [taps][n][k] -> TMA dims (k, n, taps); in PAIR mode each CTA loads half of the N tile
   CUtensorMap tmB;
   uint64_t bd[3] = {p->k, p->n, p->taps};
   uint64_t bs[2] = {(uint64_t)p->k * 2, (uint64_t)p->k * 2 * p->n};
-  uint32_t bb[3] = {64, (uint32_t)BN, 1};
+  uint32_t bb[3] = {64, (uint32_t)Cfg::B_ROWS, 1};
   if (encode_tmap_bf16(&tmB, p->w_ptr, 3, bd, bs, bb)) return 1;
   GemmDev dd = d;
   dd.n_tiles = (p->n + BN - 1) / BN;
@@ -543,26 +587,57 @@ static int launch(const b200svd_gemm_params* p, const CUtensorMap& tmA, const Ge
   }
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(mtgemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(mtgemm_kernel<BN, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(mtgemm)");
     attr_set = true;
   }
-  const uint64_t total = (uint64_t)dd.n_tiles * dd.m_tiles[0] * dd.m_tiles[1] * dd.m_tiles[2];
+  const uint64_t m_tiles = (uint64_t)dd.m_tiles[0] * dd.m_tiles[1] * dd.m_tiles[2];
+  const uint64_t total = (uint64_t)dd.n_tiles * (PAIR ? (m_tiles + 1) / 2 : m_tiles);  // (pair) tiles
   if (total == 0 || total > 0x7FFFFFFFull) {
     set_error("mtgemm: bad tile count %llu", (unsigned long long)total);
     return 1;
   }
-  const uint32_t sms = (uint32_t)sm_count();
-  const uint32_t grid = (uint32_t)(total < sms ? total : sms);
+  const uint32_t workers = PAIR ? (uint32_t)sm_count() / 2 : (uint32_t)sm_count();  // CTAs, or CTA pairs
+  const uint32_t nw = (uint32_t)(total < workers ? total : workers);
   dd.total_tiles = (uint32_t)total;
-  dd.tiles_per_cta = (uint32_t)((total + grid - 1) / grid);
-  const uint32_t grid_used = (uint32_t)((total + dd.tiles_per_cta - 1) / dd.tiles_per_cta);
-  mtgemm_kernel<BN><<<grid_used, NUM_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, tmO64, tmO32, tmR64, tmR32, dd);
-  B200_CHECK_LAUNCH("mtgemm launch");
+  dd.tiles_per_cta = (uint32_t)((total + nw - 1) / nw);
+  const uint32_t used = (uint32_t)((total + dd.tiles_per_cta - 1) / dd.tiles_per_cta);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(PAIR ? 2 * used : used);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = PAIR ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, mtgemm_kernel<BN, PAIR>, tmA, tmB, tmO64, tmO32, tmR64, tmR32, dd);
+  if (e != cudaSuccess) return cuda_fail(e, "mtgemm launch");
   return 0;
 }
 
+// 0 = never, 1 = always (when the tile shape allows), 2 = auto (compute-heavy launches); env B200SVD_PAIR
+static int g_pair_mode = -1;
+static int pair_mode() {
+  if (g_pair_mode < 0) {
+    const char* e = getenv("B200SVD_PAIR");
+    g_pair_mode = e ? atoi(e) : 2;
+    if (g_pair_mode < 0 || g_pair_mode > 2) g_pair_mode = 2;
+  }
+  return g_pair_mode;
+}
+
 }  // namespace b200
+
+extern "C" int b200svd_gemm_pair_mode(int mode) {
+  const int prev = b200::pair_mode();
+  if (mode >= 0 && mode <= 2) b200::g_pair_mode = mode;
+  return prev;
+}
 
 extern "C" int b200svd_gemm(const b200svd_gemm_params* p, void* stream) {
   using namespace b200;
@@ -667,12 +742,17 @@ extern "C" int b200svd_gemm(const b200svd_gemm_params* p, void* stream) {
   CUtensorMap tmA;
   if (encode_tmap_bf16(&tmA, p->a_ptr, 5, p->a_dims, p->a_strides, p->a_box)) return 1;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  // 2-SM (cta_group::2) tiles whenever a wide tile has at least two M tiles: measured neutral-to-better on every
+  // shape of the denoiser (profiles/r01_pair_shapes.txt); mode 1 additionally pairs the 128-wide tile
+  const uint64_t m_tiles_all = (uint64_t)d.m_tiles[0] * d.m_tiles[1] * d.m_tiles[2];
+  const int pm = pair_mode();
+  const bool pair = m_tiles_all >= 2 && ((pm >= 1 && (bn == 256 || bn == 160)) || (pm == 1 && bn == 128));
   switch (bn) {
-    case 32: return launch<32>(p, tmA, d, st);
-    case 64: return launch<64>(p, tmA, d, st);
-    case 128: return launch<128>(p, tmA, d, st);
-    case 160: return launch<160>(p, tmA, d, st);
-    case 256: return launch<256>(p, tmA, d, st);
+    case 32: return launch<32, false>(p, tmA, d, st);
+    case 64: return launch<64, false>(p, tmA, d, st);
+    case 128: return pair ? launch<128, true>(p, tmA, d, st) : launch<128, false>(p, tmA, d, st);
+    case 160: return pair ? launch<160, true>(p, tmA, d, st) : launch<160, false>(p, tmA, d, st);
+    case 256: return pair ? launch<256, true>(p, tmA, d, st) : launch<256, false>(p, tmA, d, st);
     default: set_error("b200svd_gemm: unsupported N tile %d", bn); return 1;
   }
 }

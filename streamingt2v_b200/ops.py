@@ -23,6 +23,12 @@ def launches() -> int:
     return _launch_count
 
 
+def gemm_pair_mode(mode: int = -1) -> int:
+    """Set when the wide GEMM tiles run as 2-SM (cta_group::2) tiles: 0 never, 1 whenever possible, 2 automatic.
+    Any other value only queries.  Returns the previous mode."""
+    return int(_lib.load().b200svd_gemm_pair_mode(int(mode)))
+
+
 class profile:
     """Context manager: brackets every launch with CUDA events on the launching stream and returns per-family
     (launches, total ms, algorithmic FLOPs, algorithmic bytes).  Used by bench.py for the live roofline numbers;

@@ -9,6 +9,15 @@ import torch.nn.functional as F
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=[0, 1], ids=["1sm", "2sm"])
+def pair_mode(request, cuda_dev):
+    """Every case runs with the single-CTA tiles only and with the CTA-pair (cta_group::2) tiles forced on."""
+    from streamingt2v_b200 import ops
+    prev = ops.gemm_pair_mode(request.param)
+    yield request.param
+    ops.gemm_pair_mode(prev)
+
+
 def _check(out, ref, name, rtol=2 ** -7, atol=2e-2):
     out = out.float()
     err = (out - ref).abs()
@@ -35,6 +44,27 @@ def test_linear(cuda_dev, M, K, N, bn):
     torch.cuda.synchronize()
     ref = x.float() @ w.float().t() + b
     _check(out, ref, f"linear M{M} K{K} N{N} bn{bn}")
+
+
+@pytest.mark.parametrize("M,K,N,bn", [(1357, 1280, 1280, 256), (384, 640, 640, 160), (129, 1280, 512, 256),
+                                      (128 * 149 * 2 + 5, 320, 320, 160), (5000, 1280, 1000, 256)])
+def test_wide_tiles_epilogue(cuda_dev, M, K, N, bn):
+    """160/256-wide tiles (CTA pairs in the 2sm run): odd M-tile counts, ragged N, several tiles per CTA, all
+    epilogue operands."""
+    from streamingt2v_b200 import ops, packing
+    rpf = 64
+    x = _rand((M, K), cuda_dev, seed=1)
+    w = _rand((N, K), cuda_dev, K ** -0.5, seed=2)
+    b = torch.randn(N, device=cuda_dev)
+    fvec = torch.randn((M + rpf - 1) // rpf, N, device=cuda_dev)
+    r1 = _rand((M, N), cuda_dev, seed=3)
+    r2 = _rand((M, N), cuda_dev, seed=4)
+    out = ops.linear(x, packing.pack_linear(w, cuda_dev), b, act=ops.ACT_GELU, fvec=fvec, rows_per_frame=rpf,
+                     s_acc=0.5, res1=r1, s1=0.7, res2=r2, s2=-0.5, bn=bn)
+    torch.cuda.synchronize()
+    v = x.float() @ w.float().t() + b + fvec.repeat_interleave(rpf, 0)[:M]
+    ref = 0.5 * F.gelu(v) + 0.7 * r1.float() - 0.5 * r2.float()
+    _check(out, ref, f"wide tile M{M} K{K} N{N} bn{bn}")
 
 
 def test_linear_epilogue(cuda_dev):

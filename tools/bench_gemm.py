@@ -60,7 +60,8 @@ def main():
         res.append(dict(name=name, ms=ms, tflops=fl / ms / 1e9, cudnn_ms=ref_ms, cudnn_tflops=fl / ref_ms / 1e9))
         print(res[-1], flush=True)
     os.makedirs("gpurun_out", exist_ok=True)
-    json.dump(res, open("gpurun_out/bench_gemm.json", "w"), indent=1)
+    tag = os.environ.get("B200SVD_BENCH_TAG", "")
+    json.dump(res, open(f"gpurun_out/bench_gemm{tag}.json", "w"), indent=1)
 
 
 if __name__ == "__main__":
