@@ -1,4 +1,4 @@
-// Multi-tap tensor-core GEMM for sm_100a (v3).
+// Multi-tap tensor-core GEMM for sm_100a (v4).
 // TMA (rank-5 activation view) -> smem (128B swizzle) -> tcgen05.mma (fp32 accumulators in TMEM, double buffered)
 // -> fused epilogue -> swizzled smem staging -> TMA store.  See include/b200svd.h for the contract.
 //
@@ -9,17 +9,21 @@
 //   + their elementwise neighbours (bias, emb add openaimodel.py:346-352, GEGLU attention.py:94-101,
 //     residual / AlphaBlender diffusionmodules/util.py:358-370).
 //
-// One persistent CTA per SM walks a contiguous run of 128 x BN output tiles (N tile fastest).  20 warps:
+// Persistent CTAs (one per SM; CTA pairs for the 2-SM tiles) walk a contiguous run of output tiles (N tile fastest).
+// 18 warps:
 //   warp 0       TMA producer for A/B (stage ring runs ahead across tiles)
 //   warp 1       MMA issuer + TMEM owner (two accumulator buffers: tile i's epilogue overlaps tile i+1's main loop)
-//   warp 2       TMA producer for the residual operand (ring of 3 sub-tile buffers, runs ahead of the epilogue)
-//   warps 4..19  epilogue: 4 per TMEM lane quadrant, 16 columns each per 64-column sub-tile; results are written
-//                thread-per-row into 128B/64B-swizzled staging (bank-conflict free) and leave through one TMA store
-//                per quadrant and sub-tile (hardware clips ragged edges) — no per-element address arithmetic.
-// Why: ncu on v2 (profiles/r01_ncu_gemm_*) showed the small-K layers bound by epilogue instruction issue
-// (runtime division + 64-bit addressing in copy loops, IEEE divide / erff in activations) and shared-memory bank
-// conflicts, and the large-K layers by shared-memory bandwidth per FLOP; v3 removes the former and offers a
-// 256-wide tile for the latter.
+//   warps 2..17  epilogue: the CTA's output is a stream of (tile, 64-column sub-tile) blocks; each warp owns one TMEM
+//                lane quadrant of every 4th block, start to finish, and never synchronises with another warp:
+//                residual block -> (TMA) -> private 4 KB staging block; TMEM -> registers -> bias / activation /
+//                residual (in place) -> 128B/64B-swizzled staging (bank-conflict free) -> one TMA store (hardware
+//                clips ragged edges).
+// 2-SM mode (template PAIR): a cluster of two CTAs computes a 256 x BN tile with tcgen05 cta_group::2 MMAs issued by
+// the leader CTA; each CTA stages its own 128 A rows and HALF of the B tile, commits are multicast to both CTAs.
+// Why (ncu, profiles/r01_ncu_gemm_*): v2 was bound by epilogue instruction issue and bank conflicts; v3's 16-column
+// per-warp work items spent >90% of issued instructions on waits and index arithmetic and kept the four warps of a
+// quadrant in lock-step through a named barrier; the large-K layers were bound by shared-memory bandwidth per FLOP,
+// which the pair tiles halve for B.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <stdlib.h>
@@ -64,10 +68,8 @@ constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
 constexpr int EPI_WARPS = 16;
-constexpr int FIRST_EPI_WARP = 4;
-constexpr int NUM_THREADS = (FIRST_EPI_WARP + EPI_WARPS) * 32;  // 640
-constexpr int RES_BUFS = 3;
-constexpr int RES_BUF_BYTES = 128 * 64 * 2;  // one 128-row x 64-column bf16 sub-tile
+constexpr int FIRST_EPI_WARP = 2;
+constexpr int NUM_THREADS = (FIRST_EPI_WARP + EPI_WARPS) * 32;  // 576 (register cap 112 per thread)
 constexpr int OUT_BUF_BYTES = 32 * 64 * 2;   // one quadrant (32 rows) x 64 columns
 
 template <int BN, bool PAIR>
@@ -80,15 +82,12 @@ struct TileCfg {
   static constexpr int ACC_STRIDE = (BN <= 32) ? 32 : (BN <= 64) ? 64 : (BN <= 128) ? 128 : 256;
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
   static constexpr int NSUB = (BN + 63) / 64;
-  // staging buffers per quadrant: 3 lets the TMA store of sub-tile i drain while sub-tile i+1 is being written
-  // (bulk wait_group.read 1); the single-CTA 256-wide tile only has room for 2 (wait_group.read 0)
-  static constexpr int OUT_BUFS = (BN >= 256 && !PAIR) ? 2 : 3;
-  static constexpr int OUT_BYTES = 4 * OUT_BUFS * OUT_BUF_BYTES;
-  static constexpr int FIXED_BYTES = RES_BUFS * RES_BUF_BYTES + OUT_BYTES + 512;
+  static constexpr int OUT_BYTES = EPI_WARPS * OUT_BUF_BYTES;  // one private 32-row x 64-column staging block per warp
+  static constexpr int FIXED_BYTES = OUT_BYTES + 512;
   static constexpr int STAGES_FIT = (232448 - FIXED_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_FIT > 6 ? 6 : STAGES_FIT;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + FIXED_BYTES;
-  static_assert(STAGES >= 3, "pipeline depth");
+  static_assert(STAGES >= 2, "pipeline depth");
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
   static_assert(STAGE_BYTES % 1024 == 0, "stage alignment");
 };
@@ -117,15 +116,14 @@ mtgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ __align__(1024) uint8_t smem[];  // SWIZZLE_128B operands need 1024-byte alignment
   if ((smem_u32(smem) & 1023u) != 0) __trap();
-  uint8_t* res_base = smem + STAGES * Cfg::STAGE_BYTES;
-  uint8_t* out_base = res_base + RES_BUFS * RES_BUF_BYTES;
+  uint8_t* out_base = smem + STAGES * Cfg::STAGE_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(out_base + Cfg::OUT_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* acc_full = empty_bar + STAGES;    // [2]
   uint64_t* acc_empty = acc_full + 2;         // [2]
-  uint64_t* res_full = acc_empty + 2;         // [RES_BUFS]
-  uint64_t* res_empty = res_full + RES_BUFS;  // [RES_BUFS]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_empty + RES_BUFS);
+  uint64_t* res_bar = acc_empty + 2;          // [EPI_WARPS] residual block landed in the warp's staging block
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + EPI_WARPS);
+  static_assert((2 * STAGES + 4 + EPI_WARPS) * 8 + 4 <= 512, "barrier area");
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -154,10 +152,7 @@ mtgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       mbar_init(&acc_full[b], 1);
       mbar_init(&acc_empty[b], PAIR ? 2 * EPI_WARPS : EPI_WARPS);  // one arrive per epilogue warp (of both CTAs)
     }
-    for (int b = 0; b < RES_BUFS; ++b) {
-      mbar_init(&res_full[b], 1);
-      mbar_init(&res_empty[b], EPI_WARPS);
-    }
+    for (int b = 0; b < EPI_WARPS; ++b) mbar_init(&res_bar[b], 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -250,47 +245,52 @@ mtgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       }
     }
     __syncwarp();
-  } else if (warp == 2) {
-    if (lane == 0 && use_res_ring) {
-      // ===================== TMA producer (residual sub-tiles) =====================
-      uint32_t rcount = 0;
-      for (uint32_t tile = tile_begin; tile < tile_end; ++tile) {
-        uint32_t n_tile, mb1, mb2, mb3;
-        decode_tile(p, tile, PAIR ? 2u : 1u, rank, n_tile, mb1, mb2, mb3);
-        const uint32_t otile0 = n_tile * tile_out_w;
-        for (uint32_t s = 0; s < nsub_out; ++s) {
-          const uint32_t ocol0 = otile0 + 64 * s;
-          if (ocol0 >= n_out) break;
-          const uint32_t rem = tile_out_w - 64 * s;
-          const uint32_t subw = rem >= 64 ? 64u : rem;
-          const uint32_t rb = rcount % RES_BUFS;
-          mbar_wait(&res_empty[rb], ((rcount / RES_BUFS) & 1) ^ 1);
-          mbar_expect_tx(&res_full[rb], subw * 2 * 128);
-          tma_load_5d(res_base + rb * RES_BUF_BYTES, subw == 64 ? &tmR64 : &tmR32, &res_full[rb], (int)ocol0, (int)mb1,
-                      (int)mb2, (int)mb3, 0);
-          ++rcount;
-        }
-      }
-    }
   } else if (warp >= FIRST_EPI_WARP) {
-    // ===================== epilogue warps (4..19) =====================
+    // ===================== epilogue warps (2..17) =====================
+    // The output of the CTA is a stream of blocks (tile, 64-column sub-tile); warp (q, g) owns TMEM lane quadrant q of
+    // every block n with n % 4 == g, start to finish: residual block -> (TMA) -> private staging block; TMEM ->
+    // registers -> math (+ residual, in place) -> staging -> TMA store.  Warps never synchronise with each other, so
+    // the four warps of a scheduler hide each other's latencies.  Every warp observes acc_full and arrives on
+    // acc_empty for EVERY tile (also those it owns no block of): mbarrier parity waits are only unambiguous for a
+    // waiter that is at most one phase behind.
     const int e = warp - FIRST_EPI_WARP;
-    const int q = e & 3;   // TMEM lane quadrant (== warp % 4)
-    const int g = e >> 2;  // 16-column group inside every 64-column sub-tile
+    const int q = warp & 3;  // TMEM lane quadrant (hardware: warp % 4)
+    const int g = e >> 2;    // block phase; warps 4g+2 .. 4g+5 cover the four quadrants once
     const int r = q * 32 + lane;
     const uint32_t lb1 = p.m_lb[0], lb2 = p.m_lb[1];
     const uint32_t qoff = (uint32_t)(q * 32);
     const uint32_t qo1 = qoff & ((1u << lb1) - 1);
     const uint32_t qo2 = (qoff >> lb1) & ((1u << lb2) - 1);
     const uint32_t qo3 = qoff >> (lb1 + lb2);
-    uint8_t* outq = out_base + q * Cfg::OUT_BUFS * OUT_BUF_BYTES;
+    uint8_t* ob = out_base + e * OUT_BUF_BYTES;
+    uint64_t* my_res = &res_bar[e];
     const bool bias_vec = p.bias != nullptr && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0;
     const bool fvec_vec = p.fvec != nullptr && (reinterpret_cast<uintptr_t>(p.fvec) & 15) == 0 && (p.ldf & 3) == 0;
+    const uint32_t num_tiles = tile_end > tile_begin ? tile_end - tile_begin : 0u;
 
-    uint32_t tcount = 0, ocount = 0, rcount = 0;
-    for (uint32_t tile = tile_begin; tile < tile_end; ++tile, ++tcount) {
-      uint32_t n_tile, mb1, mb2, mb3;
-      decode_tile(p, tile, PAIR ? 2u : 1u, rank, n_tile, mb1, mb2, mb3);
+    uint32_t tcount = 0, s = (uint32_t)g, tpass = 0, rcount = 0;
+    while (s >= nsub_out) {
+      s -= nsub_out;
+      ++tcount;
+    }
+    uint32_t n_tile = 0, mb1 = 0, mb2 = 0, mb3 = 0;
+    // residual block of (tile, s) -> staging block; the previous store must have finished reading it
+    auto prefetch_residual = [&]() {
+      const uint32_t ocol0 = n_tile * tile_out_w + 64 * s;
+      if (use_res_ring && ocol0 < n_out && lane == 0) {
+        const uint32_t rem = tile_out_w - 64 * s;
+        const uint32_t subw = rem >= 64 ? 64u : rem;
+        tma_store_wait_read<0>();
+        mbar_expect_tx(my_res, subw * 2 * 32);
+        tma_load_5d(ob, subw == 64 ? &tmR64 : &tmR32, my_res, (int)ocol0, (int)(mb1 + qo1), (int)(mb2 + qo2),
+                    (int)(mb3 + qo3), 0);
+      }
+    };
+    if (tcount < num_tiles) {
+      decode_tile(p, tile_begin + tcount, PAIR ? 2u : 1u, rank, n_tile, mb1, mb2, mb3);
+      prefetch_residual();
+    }
+    while (tcount < num_tiles) {
       const uint32_t n0 = n_tile * BN;
       const uint32_t otile0 = n_tile * tile_out_w;
       const uint32_t m1 = mb1 + (r & ((1u << lb1) - 1));
@@ -299,8 +299,20 @@ mtgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       const bool valid = (m1 < p.m_ext[0]) && (m2 < p.m_ext[1]) && (m3 < p.m_ext[2]);
       const int64_t row = (int64_t)m1 * p.out_rs[0] + (int64_t)m2 * p.out_rs[1] + (int64_t)m3 * p.out_rs[2];
       const float* fv = nullptr;
-      if (p.fvec != nullptr && valid) fv = p.fvec + (row / p.rows_per_frame) * p.ldf;
+      if (p.fvec != nullptr && valid) fv = p.fvec + (int64_t)((uint32_t)row / p.rows_per_frame) * p.ldf;
+      const uint32_t ocol0 = otile0 + 64 * s;
+      const bool skip = ocol0 >= n_out;  // block beyond the ragged N edge (warp-uniform)
+      const uint32_t rem = tile_out_w - 64 * s;
+      const uint32_t subw = rem >= 64 ? 64u : rem;  // 64 or 32 (direct path: also narrower tiles)
 
+      // release the accumulators of the tiles this warp owns no block of
+      for (; tpass < tcount; ++tpass) {
+        mbar_wait(&acc_full[tpass & 1], (tpass >> 1) & 1);
+        if (lane == 0) {
+          if (PAIR) mbar_arrive_leader(&acc_empty[tpass & 1]);
+          else mbar_arrive(&acc_empty[tpass & 1]);
+        }
+      }
       const uint32_t b = tcount & 1;
       mbar_wait(&acc_full[b], (tcount >> 1) & 1);
       tc_fence_after();
@@ -366,125 +378,89 @@ mtgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         }
       };
 
-      if (p.tma_epi) {
-        for (uint32_t s = 0; s < nsub_out; ++s) {
-          const uint32_t ocol0 = otile0 + 64 * s;
-          if (ocol0 >= n_out) break;  // CTA-uniform (same rule in the residual producer)
-          const uint32_t rem = tile_out_w - 64 * s;
-          const uint32_t subw = rem >= 64 ? 64u : rem;  // 64 or 32
-          const bool last_sub = (s + 1 == nsub_out) || (otile0 + 64 * (s + 1) >= n_out);
-          uint32_t rb = 0;
-          if (use_res_ring) {
-            rb = rcount % RES_BUFS;
-            mbar_wait(&res_full[rb], (rcount / RES_BUFS) & 1);
-          }
-          uint8_t* ob = outq + (ocount % Cfg::OUT_BUFS) * OUT_BUF_BYTES;
-          if ((uint32_t)(16 * g) < subw) {
-            const uint32_t acol = 64 * s + 16 * g;  // accumulator column (value half for GEGLU)
-            uint32_t va[16], vg[16];
-            tmem_ld16(tlane + acol, va);
-            if (geglu) tmem_ld16(tlane + (uint32_t)(BN / 2) + acol, vg);
-            tmem_ld_wait();
-            float v[16];
+      if (!skip && p.tma_epi) {
+        if (use_res_ring) {
+          mbar_wait(my_res, rcount & 1);  // residual block has landed in the staging block
+          ++rcount;
+        } else {
+          if (lane == 0) tma_store_wait_read<0>();  // the previous TMA store has finished reading the staging block
+          __syncwarp();
+        }
+        uint8_t* orow;
+        uint32_t x;  // swizzle phase of this thread's staging row
+        if (subw == 64) {
+          orow = ob + lane * 128;
+          x = (uint32_t)(lane & 7);
+        } else {
+          orow = ob + lane * 64;
+          x = (uint32_t)((lane >> 1) & 3);
+        }
+        const uint32_t nchunks = subw >> 4;
+#pragma unroll 1
+        for (uint32_t c = 0; c < nchunks; ++c) {
+          const uint32_t acol = 64 * s + 16 * c;  // accumulator column (value half for GEGLU)
+          uint32_t va[16], vg[16];
+          tmem_ld16(tlane + acol, va);
+          if (geglu) tmem_ld16(tlane + (uint32_t)(BN / 2) + acol, vg);
+          tmem_ld_wait();
+          float v[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(va[j]);
-            const uint32_t ocol = ocol0 + 16 * g;
-            const bool full = (ocol + 16) <= n_out;
-            finish16(v, vg, n0 + acol, ocol, full);
-            // swizzled 16-byte chunk positions of this thread's two chunks (c = 2g, 2g+1)
-            const uint32_t c_lo = 2 * g, c_hi = 2 * g + 1;
-            if (use_res_ring) {
-              const uint8_t* rrow;
-              uint32_t x;
-              if (subw == 64) {
-                rrow = res_base + rb * RES_BUF_BYTES + r * 128;
-                x = (uint32_t)(r & 7);
-              } else {
-                rrow = res_base + rb * RES_BUF_BYTES + r * 64;
-                x = (uint32_t)((r >> 1) & 3);
-              }
-              const uint4 a = *reinterpret_cast<const uint4*>(rrow + ((c_lo ^ x) << 4));
-              const uint4 bq = *reinterpret_cast<const uint4*>(rrow + ((c_hi ^ x) << 4));
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(va[j]);
+          const uint32_t ocol = ocol0 + 16 * c;
+          const bool full = (ocol + 16) <= n_out;
+          finish16(v, vg, n0 + acol, ocol, full);
+          const uint32_t c_lo = 2 * c, c_hi = 2 * c + 1;  // 16-byte chunks of the row
+          if (use_res_ring) {
+            // residual chunk sits where the result will go (same box, same swizzle): read, add, overwrite
+            const uint4 a = *reinterpret_cast<const uint4*>(orow + ((c_lo ^ x) << 4));
+            const uint4 bq = *reinterpret_cast<const uint4*>(orow + ((c_hi ^ x) << 4));
+            const uint32_t w[8] = {a.x, a.y, a.z, a.w, bq.x, bq.y, bq.z, bq.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              v[2 * j] += p.s1 * bf16_lo(w[j]);
+              v[2 * j + 1] += p.s1 * bf16_hi(w[j]);
+            }
+          }
+          if (p.res2 != nullptr && valid) {
+            // second residual (only the temporal AlphaBlender GEMMs): read straight from global, own row
+            const __nv_bfloat16* rp = p.res2 + row * p.ld2 + ocol;
+            if (full) {
+              const uint4 a = __ldg(reinterpret_cast<const uint4*>(rp));
+              const uint4 bq = __ldg(reinterpret_cast<const uint4*>(rp) + 1);
               const uint32_t w[8] = {a.x, a.y, a.z, a.w, bq.x, bq.y, bq.z, bq.w};
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
-                v[2 * j] += p.s1 * bf16_lo(w[j]);
-                v[2 * j + 1] += p.s1 * bf16_hi(w[j]);
+                v[2 * j] += p.s2 * bf16_lo(w[j]);
+                v[2 * j + 1] += p.s2 * bf16_hi(w[j]);
               }
-            }
-            if (p.res2 != nullptr && valid) {
-              // second residual (only the temporal AlphaBlender GEMMs): read straight from global, own row
-              const __nv_bfloat16* rp = p.res2 + row * p.ld2 + ocol;
-              if (full) {
-                const uint4 a = __ldg(reinterpret_cast<const uint4*>(rp));
-                const uint4 bq = __ldg(reinterpret_cast<const uint4*>(rp) + 1);
-                const uint32_t w[8] = {a.x, a.y, a.z, a.w, bq.x, bq.y, bq.z, bq.w};
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  v[2 * j] += p.s2 * bf16_lo(w[j]);
-                  v[2 * j + 1] += p.s2 * bf16_hi(w[j]);
-                }
-              } else {
-                for (int j = 0; j < 16; ++j)
-                  if (ocol + j < n_out) v[j] += p.s2 * __bfloat162float(rp[j]);
-              }
-            }
-            uint8_t* orow;
-            uint32_t xo;
-            if (subw == 64) {
-              orow = ob + lane * 128;
-              xo = (uint32_t)(lane & 7);
             } else {
-              orow = ob + lane * 64;
-              xo = (uint32_t)((lane >> 1) & 3);
-            }
-            *reinterpret_cast<uint4*>(orow + ((c_lo ^ xo) << 4)) =
-                make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-            *reinterpret_cast<uint4*>(orow + ((c_hi ^ xo) << 4)) =
-                make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]),
-                           pack_bf16x2(v[14], v[15]));
-            fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA store
-          }
-          if (use_res_ring) {
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&res_empty[rb]);
-            ++rcount;
-          }
-          if (last_sub) {
-            // last TMEM read of this tile is done: hand the accumulator buffer back before the store
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-              if (PAIR) mbar_arrive_leader(&acc_empty[b]);
-              else mbar_arrive(&acc_empty[b]);
+              for (int j = 0; j < 16; ++j)
+                if (ocol + j < n_out) v[j] += p.s2 * __bfloat162float(rp[j]);
             }
           }
-          named_bar_sync(1 + q, 128);  // the quadrant's 32 x subw block is complete in staging
-          if (g == 0 && lane == 0) {
-            tma_store_5d(subw == 64 ? &tmO64 : &tmO32, ob, (int)ocol0, (int)(mb1 + qo1), (int)(mb2 + qo2),
-                         (int)(mb3 + qo3), 0);
-            tma_store_commit();
-            // all but the newest OUT_BUFS-2 stores have finished reading: the buffer written next-but-one is free
-            // by the time its writers pass the next named barrier
-            tma_store_wait_read<Cfg::OUT_BUFS - 2>();
-          }
-          ++ocount;
+          *reinterpret_cast<uint4*>(orow + ((c_lo ^ x) << 4)) =
+              make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+          *reinterpret_cast<uint4*>(orow + ((c_hi ^ x) << 4)) =
+              make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]),
+                         pack_bf16x2(v[14], v[15]));
         }
-      } else {
-        // direct epilogue: fp32 outputs (tiny GEMMs: embeddings, conv_out)
-        for (uint32_t c0 = 16 * g; c0 < tile_out_w; c0 += 64) {
-          if (otile0 + c0 >= n_out) break;
+        fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA store
+      } else if (!skip) {
+        // direct epilogue: fp32 outputs (tiny GEMMs: embeddings, conv_out, attention scores)
+        for (uint32_t c0 = 0; c0 < subw; c0 += 16) {
+          const uint32_t acol = 64 * s + c0;
+          if (otile0 + acol >= n_out) break;
           uint32_t va[16], vg[16];
-          tmem_ld16(tlane + c0, va);
-          if (geglu) tmem_ld16(tlane + (uint32_t)(BN / 2) + c0, vg);
+          tmem_ld16(tlane + acol, va);
+          if (geglu) tmem_ld16(tlane + (uint32_t)(BN / 2) + acol, vg);
           tmem_ld_wait();
           if (!valid) continue;
           float v[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(va[j]);
-          const uint32_t ocol = otile0 + c0;
+          const uint32_t ocol = otile0 + acol;
           const bool full = (ocol + 16 <= n_out);
-          finish16(v, vg, n0 + c0, ocol, full);
+          finish16(v, vg, n0 + acol, ocol, full);
           if (p.res1 != nullptr) {
             const __nv_bfloat16* rp = p.res1 + row * p.ld1 + ocol;
             for (int j = 0; j < 16; ++j)
@@ -505,15 +481,39 @@ mtgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
               if (full || ocol + j < n_out) op[j] = __float2bfloat16(v[j]);
           }
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          if (PAIR) mbar_arrive_leader(&acc_empty[b]);
-          else mbar_arrive(&acc_empty[b]);
+      }
+      // this block's TMEM reads are done: hand the accumulator back, then store
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_leader(&acc_empty[b]);
+        else mbar_arrive(&acc_empty[b]);
+        if (!skip && p.tma_epi) {
+          tma_store_5d(subw == 64 ? &tmO64 : &tmO32, ob, (int)ocol0, (int)(mb1 + qo1), (int)(mb2 + qo2),
+                       (int)(mb3 + qo3), 0);
+          tma_store_commit();
         }
       }
+      tpass = tcount + 1;
+      s += 4;
+      const uint32_t tprev = tcount;
+      while (s >= nsub_out) {
+        s -= nsub_out;
+        ++tcount;
+      }
+      if (tcount < num_tiles) {
+        if (tcount != tprev) decode_tile(p, tile_begin + tcount, PAIR ? 2u : 1u, rank, n_tile, mb1, mb2, mb3);
+        prefetch_residual();
+      }
     }
-    if (p.tma_epi && g == 0 && lane == 0) tma_store_wait_all();  // all bulk stores of this thread have landed
+    for (; tpass < num_tiles; ++tpass) {
+      mbar_wait(&acc_full[tpass & 1], (tpass >> 1) & 1);
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_leader(&acc_empty[tpass & 1]);
+        else mbar_arrive(&acc_empty[tpass & 1]);
+      }
+    }
+    if (p.tma_epi && lane == 0) tma_store_wait_all();  // all bulk stores of this thread have landed
   }
 
   tc_fence_before();
@@ -565,7 +565,7 @@ static int launch(const b200svd_gemm_params* p, const CUtensorMap& tmA, const Ge
   GemmDev dd = d;
   dd.n_tiles = (p->n + BN - 1) / BN;
 
-  // epilogue tensor maps: output (quadrant boxes of 32 rows) and residual-1 (full 128-row boxes)
+  // epilogue tensor maps: output and residual-1, both in quadrant boxes of 32 rows
   CUtensorMap tmO64, tmO32, tmR64, tmR32;
   memset(&tmO64, 0, sizeof(tmO64));
   tmO32 = tmO64;
@@ -581,8 +581,8 @@ static int launch(const b200svd_gemm_params* p, const CUtensorMap& tmA, const Ge
     if (encode_rows_view(&tmO64, p->out, p->ldo, n_out, p->m_ext, p->out_rs, qbox, 64)) return 1;
     if (encode_rows_view(&tmO32, p->out, p->ldo, n_out, p->m_ext, p->out_rs, qbox, 32)) return 1;
     if (p->res1 != nullptr) {
-      if (encode_rows_view(&tmR64, p->res1, p->ld1, n_out, p->m_ext, p->out_rs, p->m_box, 64)) return 1;
-      if (encode_rows_view(&tmR32, p->res1, p->ld1, n_out, p->m_ext, p->out_rs, p->m_box, 32)) return 1;
+      if (encode_rows_view(&tmR64, p->res1, p->ld1, n_out, p->m_ext, p->out_rs, qbox, 64)) return 1;
+      if (encode_rows_view(&tmR32, p->res1, p->ld1, n_out, p->m_ext, p->out_rs, qbox, 32)) return 1;
     }
   }
   static bool attr_set = false;
