@@ -23,6 +23,7 @@
 // 2^8 (then O and l are rescaled once, by the same softmax threads); probabilities are therefore bounded by 2^8
 // instead of 1, which bf16 represents exactly as well, and the final O / l is unchanged.
 #include <cuda.h>
+#include <stdlib.h>
 #include <cuda_bf16.h>
 #include <math.h>
 
@@ -42,6 +43,8 @@ constexpr int FA_SMEM_BYTES = 2 * FA_Q_BYTES + FA_KV_STAGES * 2 * FA_KV_TILE_BYT
 constexpr int FA_TMEM_COLS = 512;  // score buffers [0,128) [128,256) [256,384) (P aliases the first 64 columns), O_A [384,448) O_B [448,512)
 constexpr int FA_THREADS = 10 * 32;
 constexpr float FA_RESCALE_THRESHOLD = 8.0f;  // log2 units
+constexpr int FA_POLY_DEFAULT = 0;  // measured (tools/bench_fa.py): every 1/8 moved to the FMA pipe costs ~5%: the softmax
+                                    // warps are bound by their own dependent-latency chain, not by MUFU throughput
 
 struct FaParams {
   __nv_bfloat16* out;
@@ -50,6 +53,9 @@ struct FaParams {
   float scale_log2;
 };
 
+// POLY: how many of every 8 score pairs take their exp2 on the FMA pipe (ex2_poly) instead of MUFU.  The softmax
+// of a 128 x 128 tile needs 2x the MUFU time of the tile's MMAs (16 ex2/clk/SM), so the kernel is MUFU-bound.
+template <int POLY>
 __global__ void __launch_bounds__(FA_THREADS, 1)
 flash_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const FaParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];  // SWIZZLE_128B tiles need 1024-byte alignment
@@ -227,8 +233,16 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const FaParams p) {
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          float a = ex2_approx(fmaf(__uint_as_float(sv[2 * i]), c, -mb));
-          float b = ex2_approx(fmaf(__uint_as_float(sv[2 * i + 1]), c, -mb));
+          const float xa = fmaf(__uint_as_float(sv[2 * i]), c, -mb);
+          const float xb = fmaf(__uint_as_float(sv[2 * i + 1]), c, -mb);
+          float a, b;
+          if ((i & 7) < POLY) {
+            a = ex2_poly(xa);
+            b = ex2_poly(xb);
+          } else {
+            a = ex2_approx(xa);
+            b = ex2_approx(xb);
+          }
           if (tail) {
             if (kbase + c0 + 2 * i >= p.S) a = 0.f;
             if (kbase + c0 + 2 * i + 1 >= p.S) b = 0.f;
@@ -305,11 +319,25 @@ extern "C" int b200svd_flash_attn(const void* qkv, int64_t ldqkv, void* out, int
   uint64_t strides[2] = {(uint64_t)ldqkv * 2, (uint64_t)ldqkv * 2 * (uint64_t)s};
   uint32_t box[3] = {64, 128, 1};
   if (encode_tmap_bf16(&tm, qkv, 3, dims, strides, box)) return 1;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(flash_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_BYTES);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(flash_attn)");
-    attr_set = true;
+  // exp2 split between MUFU and the FMA pipe: B200SVD_FA_POLY = 0..4 of every 8 score pairs (tuning knob)
+  static int poly = -1;
+  if (poly < 0) {
+    const char* ev = getenv("B200SVD_FA_POLY");
+    poly = ev ? atoi(ev) : FA_POLY_DEFAULT;
+    if (poly < 0 || poly > 4) poly = FA_POLY_DEFAULT;
+    cudaError_t e = cudaSuccess;
+    auto set = [&](auto kern) {
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_BYTES);
+    };
+    set(flash_attn_kernel<0>);
+    set(flash_attn_kernel<1>);
+    set(flash_attn_kernel<2>);
+    set(flash_attn_kernel<3>);
+    set(flash_attn_kernel<4>);
+    if (e != cudaSuccess) {
+      poly = -1;
+      return cuda_fail(e, "cudaFuncSetAttribute(flash_attn)");
+    }
   }
   FaParams p;
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
@@ -319,7 +347,14 @@ extern "C" int b200svd_flash_attn(const void* qkv, int64_t ldqkv, void* out, int
   p.C = C;
   p.scale_log2 = scale * 1.4426950408889634f;
   dim3 grid((s + 2 * FA_BQ - 1) / (2 * FA_BQ), heads, n);
-  flash_attn_kernel<<<grid, FA_THREADS, FA_SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream)>>>(tm, p);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  switch (poly) {
+    case 0: flash_attn_kernel<0><<<grid, FA_THREADS, FA_SMEM_BYTES, st>>>(tm, p); break;
+    case 1: flash_attn_kernel<1><<<grid, FA_THREADS, FA_SMEM_BYTES, st>>>(tm, p); break;
+    case 2: flash_attn_kernel<2><<<grid, FA_THREADS, FA_SMEM_BYTES, st>>>(tm, p); break;
+    case 3: flash_attn_kernel<3><<<grid, FA_THREADS, FA_SMEM_BYTES, st>>>(tm, p); break;
+    default: flash_attn_kernel<4><<<grid, FA_THREADS, FA_SMEM_BYTES, st>>>(tm, p); break;
+  }
   B200_CHECK_LAUNCH("flash_attn");
   return 0;
 }

@@ -41,6 +41,7 @@ struct GemmDev {
   uint32_t n;  // GEMM N (weight rows)
   uint32_t n_tiles;
   uint32_t total_tiles, tiles_per_cta;
+  uint32_t a_half_dim, a_half_size;  // QUAD: A-view dim whose box is halved, and the half extent
   uint32_t m_ext[3];
   uint32_t m_lb[3];  // log2 of box
   uint32_t m_tiles[3];
@@ -72,8 +73,9 @@ constexpr int FIRST_EPI_WARP = 2;
 constexpr int NUM_THREADS = (FIRST_EPI_WARP + EPI_WARPS) * 32;  // 576 (register cap 112 per thread)
 constexpr int OUT_BUF_BYTES = 32 * 64 * 2;   // one quadrant (32 rows) x 64 columns
 
-template <int BN, bool PAIR>
+template <int BN, int CL>
 struct TileCfg {
+  static constexpr bool PAIR = CL >= 2;
   // PAIR: two CTAs of a cluster compute a 256 x BN tile with one cta_group::2 MMA stream; each CTA stages its own
   // 128 A rows and HALF of the B tile (the tensor cores of the pair share B), which halves B traffic per FLOP.
   static constexpr int B_ROWS = PAIR ? BN / 2 : BN;
@@ -95,8 +97,9 @@ struct TileCfg {
 // `tile` enumerates (N tile fastest, then M tile) — in PAIR mode (M-tile PAIR); mrank selects this CTA's M tile of the
 // pair.  An M tile index past the end decodes to coordinates beyond the extents (all rows out of bounds).
 __device__ __forceinline__ void decode_tile(const GemmDev& p, uint32_t tile, uint32_t mmul, uint32_t mrank,
-                                            uint32_t& n_tile, uint32_t& mb1, uint32_t& mb2, uint32_t& mb3) {
-  n_tile = tile % p.n_tiles;
+                                            uint32_t nmul, uint32_t nrank, uint32_t& n_tile, uint32_t& mb1,
+                                            uint32_t& mb2, uint32_t& mb3) {
+  n_tile = (tile % p.n_tiles) * nmul + nrank;  // p.n_tiles counts N work items (pairs of N tiles in QUAD mode)
   uint32_t mt = (tile / p.n_tiles) * mmul + mrank;
   const uint32_t t1 = mt % p.m_tiles[0];
   mt /= p.m_tiles[0];
@@ -107,12 +110,15 @@ __device__ __forceinline__ void decode_tile(const GemmDev& p, uint32_t tile, uin
   mb3 = t3 << p.m_lb[2];
 }
 
-template <int BN, bool PAIR>
+template <int BN, int CL>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-mtgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+mtgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAh,
+              const __grid_constant__ CUtensorMap tmB,
               const __grid_constant__ CUtensorMap tmO64, const __grid_constant__ CUtensorMap tmO32,
               const __grid_constant__ CUtensorMap tmR64, const __grid_constant__ CUtensorMap tmR32, const GemmDev p) {
-  using Cfg = TileCfg<BN, PAIR>;
+  using Cfg = TileCfg<BN, CL>;
+  constexpr bool PAIR = CL >= 2;  // cta_group::2 tiles
+  constexpr bool QUAD = CL == 4;  // two pairs on the same A rows (adjacent N tiles): A halves multicast between them
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ __align__(1024) uint8_t smem[];  // SWIZZLE_128B operands need 1024-byte alignment
   if ((smem_u32(smem) & 1023u) != 0) __trap();
@@ -128,8 +134,10 @@ mtgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;  // 0 = leader CTA of the pair (issues the MMAs)
-  const uint32_t tile_begin = (PAIR ? (blockIdx.x >> 1) : blockIdx.x) * p.tiles_per_cta;
+  const uint32_t rank4 = PAIR ? cluster_ctarank() : 0u;
+  const uint32_t rank = rank4 & 1u;    // M tile of the pair; 0 = leader CTA (issues the MMAs)
+  const uint32_t npair = rank4 >> 1;   // QUAD: which of the two N tiles this pair computes
+  const uint32_t tile_begin = (blockIdx.x / CL) * p.tiles_per_cta;
   const uint32_t tile_end = min(tile_begin + p.tiles_per_cta, p.total_tiles);
   const bool geglu = (p.act == B200SVD_ACT_GEGLU);
   const uint32_t n_out = geglu ? p.n / 2 : p.n;
@@ -146,7 +154,7 @@ mtgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     }
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], QUAD ? 2 : 1);  // QUAD: both pairs' MMAs must have read the stage (A is shared)
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&acc_full[b], 1);
@@ -177,7 +185,7 @@ mtgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       uint32_t it = 0;
       for (uint32_t tile = tile_begin; tile < tile_end; ++tile) {
         uint32_t n_tile, mb1, mb2, mb3;
-        decode_tile(p, tile, PAIR ? 2u : 1u, rank, n_tile, mb1, mb2, mb3);
+        decode_tile(p, tile, PAIR ? 2u : 1u, rank, QUAD ? 2u : 1u, npair, n_tile, mb1, mb2, mb3);
         int base[5] = {0, 0, 0, 0, 0};
         base[p.m_adim[0]] += (int)mb1;
         base[p.m_adim[1]] += (int)mb2;
@@ -192,12 +200,21 @@ mtgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           for (uint32_t kb = 0; kb < p.kblocks; ++kb, ++it) {
             const uint32_t s = it % STAGES;
             const uint32_t ph = (it / STAGES) & 1;
-            mbar_wait(&empty_bar[s], ph ^ 1);
+            mbar_wait_parked(&empty_bar[s], ph ^ 1);
             uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
             if (PAIR) {
               // both CTAs' loads are credited to the leader's barrier; the leader expects the bytes of the pair
               if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * Cfg::STAGE_BYTES);
-              tma_load_5d_2sm(sa, &tmA, &full_bar[s], c0 + (int)(kb * BK), c1, c2, c3, c4);
+              if (QUAD) {
+                // this CTA fetches one 64-row half of the A tile and multicasts it to itself and to its twin in the
+                // other pair (same M tile, other N tile): half the L2->SM traffic for A
+                int cc[5] = {c0 + (int)(kb * BK), c1, c2, c3, c4};
+                cc[p.a_half_dim] += (int)(npair * p.a_half_size);
+                tma_load_5d_2sm_mc(sa + npair * (A_STAGE_BYTES / 2), &tmAh, &full_bar[s], cc[0], cc[1], cc[2], cc[3],
+                                   cc[4], (uint16_t)((1u << rank) | (1u << (rank + 2))));
+              } else {
+                tma_load_5d_2sm(sa, &tmA, &full_bar[s], c0 + (int)(kb * BK), c1, c2, c3, c4);
+              }
               tma_load_3d_2sm(sa + A_STAGE_BYTES, &tmB, &full_bar[s], (int)(kb * BK), n0 + (int)(rank * (BN / 2)),
                               (int)tap);
             } else {
@@ -216,7 +233,7 @@ mtgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       uint32_t it = 0, tcount = 0;
       for (uint32_t tile = tile_begin; tile < tile_end; ++tile, ++tcount) {
         const uint32_t b = tcount & 1;
-        mbar_wait(&acc_empty[b], ((tcount >> 1) & 1) ^ 1);  // epilogue has drained this accumulator buffer
+        mbar_wait_parked(&acc_empty[b], ((tcount >> 1) & 1) ^ 1);  // epilogue has drained this accumulator buffer
         tc_fence_after();
         const uint32_t tacc = tmem_base + b * Cfg::ACC_STRIDE;
         for (uint32_t i = 0; i < iters_per_tile; ++i, ++it) {
@@ -236,11 +253,12 @@ mtgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
               umma_f16_ss(tacc, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, (i > 0 || kk > 0) ? 1u : 0u);
           }
           // frees the smem stage (in both CTAs of a pair) once these MMAs have read it
-          if (PAIR) umma_commit_2sm(&empty_bar[s]);
+          if (QUAD) umma_commit_2sm(&empty_bar[s], (uint16_t)0xF);
+          else if (PAIR) umma_commit_2sm(&empty_bar[s]);
           else umma_commit(&empty_bar[s]);
         }
         // accumulator complete (signalled to the epilogue warps of both CTAs of a pair)
-        if (PAIR) umma_commit_2sm(&acc_full[b]);
+        if (PAIR) umma_commit_2sm(&acc_full[b], (uint16_t)(3u << (2 * npair)));
         else umma_commit(&acc_full[b]);
       }
     }
@@ -287,7 +305,7 @@ mtgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       }
     };
     if (tcount < num_tiles) {
-      decode_tile(p, tile_begin + tcount, PAIR ? 2u : 1u, rank, n_tile, mb1, mb2, mb3);
+      decode_tile(p, tile_begin + tcount, PAIR ? 2u : 1u, rank, QUAD ? 2u : 1u, npair, n_tile, mb1, mb2, mb3);
       prefetch_residual();
     }
     while (tcount < num_tiles) {
@@ -307,14 +325,14 @@ mtgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 
       // release the accumulators of the tiles this warp owns no block of
       for (; tpass < tcount; ++tpass) {
-        mbar_wait(&acc_full[tpass & 1], (tpass >> 1) & 1);
+        mbar_wait_parked(&acc_full[tpass & 1], (tpass >> 1) & 1);
         if (lane == 0) {
           if (PAIR) mbar_arrive_leader(&acc_empty[tpass & 1]);
           else mbar_arrive(&acc_empty[tpass & 1]);
         }
       }
       const uint32_t b = tcount & 1;
-      mbar_wait(&acc_full[b], (tcount >> 1) & 1);
+      mbar_wait_parked(&acc_full[b], (tcount >> 1) & 1);
       tc_fence_after();
       const uint32_t tlane = tmem_base + b * Cfg::ACC_STRIDE + ((uint32_t)(q * 32) << 16);
 
@@ -502,12 +520,12 @@ mtgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         ++tcount;
       }
       if (tcount < num_tiles) {
-        if (tcount != tprev) decode_tile(p, tile_begin + tcount, PAIR ? 2u : 1u, rank, n_tile, mb1, mb2, mb3);
+        if (tcount != tprev) decode_tile(p, tile_begin + tcount, PAIR ? 2u : 1u, rank, QUAD ? 2u : 1u, npair, n_tile, mb1, mb2, mb3);
         prefetch_residual();
       }
     }
     for (; tpass < num_tiles; ++tpass) {
-      mbar_wait(&acc_full[tpass & 1], (tpass >> 1) & 1);
+      mbar_wait_parked(&acc_full[tpass & 1], (tpass >> 1) & 1);
       if (lane == 0) {
         if (PAIR) mbar_arrive_leader(&acc_empty[tpass & 1]);
         else mbar_arrive(&acc_empty[tpass & 1]);
@@ -553,9 +571,11 @@ static int encode_rows_view(CUtensorMap* tm, const void* base, int64_t ld, uint3
   return box_cols == 64 ? encode_tmap_bf16(tm, base, 5, dims, str, box) : encode_tmap_bf16_sw64(tm, base, 5, dims, str, box);
 }
 
-template <int BN, bool PAIR>
+template <int BN, int CL>
 static int launch(const b200svd_gemm_params* p, const CUtensorMap& tmA, const GemmDev& d, cudaStream_t st) {
-  using Cfg = TileCfg<BN, PAIR>;
+  using Cfg = TileCfg<BN, CL>;
+  constexpr bool PAIR = CL >= 2;
+  constexpr bool QUAD = CL == 4;
   // weights [taps][n][k] -> TMA dims (k, n, taps); in PAIR mode each CTA loads half of the N tile
   CUtensorMap tmB;
   uint64_t bd[3] = {p->k, p->n, p->taps};
@@ -564,6 +584,25 @@ static int launch(const b200svd_gemm_params* p, const CUtensorMap& tmA, const Ge
   if (encode_tmap_bf16(&tmB, p->w_ptr, 3, bd, bs, bb)) return 1;
   GemmDev dd = d;
   dd.n_tiles = (p->n + BN - 1) / BN;
+  if (QUAD) dd.n_tiles = (dd.n_tiles + 1) / 2;  // N work items = pairs of N tiles
+  // QUAD: second activation map whose box is one 64-row half of the A tile (outermost non-unit row dim halved)
+  CUtensorMap tmAh = tmA;
+  dd.a_half_dim = 0;
+  dd.a_half_size = 0;
+  if (QUAD) {
+    int hd = 2;
+    while (hd > 0 && p->m_box[hd] < 2) --hd;
+    if (p->m_box[hd] < 2) {
+      set_error("mtgemm: cannot halve the A tile");
+      return 1;
+    }
+    uint32_t hb[5];
+    for (int i = 0; i < 5; ++i) hb[i] = p->a_box[i];
+    dd.a_half_dim = p->m_adim[hd];
+    dd.a_half_size = p->m_box[hd] / 2;
+    hb[dd.a_half_dim] = dd.a_half_size;
+    if (encode_tmap_bf16(&tmAh, p->a_ptr, 5, p->a_dims, p->a_strides, hb)) return 1;
+  }
 
   // epilogue tensor maps: output and residual-1, both in quadrant boxes of 32 rows
   CUtensorMap tmO64, tmO32, tmR64, tmR32;
@@ -587,7 +626,7 @@ static int launch(const b200svd_gemm_params* p, const CUtensorMap& tmA, const Ge
   }
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(mtgemm_kernel<BN, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(mtgemm_kernel<BN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(mtgemm)");
     attr_set = true;
   }
@@ -597,25 +636,49 @@ static int launch(const b200svd_gemm_params* p, const CUtensorMap& tmA, const Ge
     set_error("mtgemm: bad tile count %llu", (unsigned long long)total);
     return 1;
   }
-  const uint32_t workers = PAIR ? (uint32_t)sm_count() / 2 : (uint32_t)sm_count();  // CTAs, or CTA pairs
+  // CTAs, CTA pairs or CTA quads that can be co-resident (clusters must fit inside a GPC, so quads may not tile all SMs)
+  static int max_clusters = 0;
+  if (max_clusters == 0) {
+    max_clusters = sm_count() / CL;
+    if (CL > 1) {
+      cudaLaunchConfig_t qc;
+      memset(&qc, 0, sizeof(qc));
+      qc.gridDim = dim3((unsigned)(sm_count() / CL * CL));
+      qc.blockDim = dim3(NUM_THREADS);
+      qc.dynamicSmemBytes = Cfg::SMEM_BYTES;
+      cudaLaunchAttribute qa[1];
+      qa[0].id = cudaLaunchAttributeClusterDimension;
+      qa[0].val.clusterDim.x = CL;
+      qa[0].val.clusterDim.y = 1;
+      qa[0].val.clusterDim.z = 1;
+      qc.attrs = qa;
+      qc.numAttrs = 1;
+      int nc = 0;
+      if (cudaOccupancyMaxActiveClusters(&nc, mtgemm_kernel<BN, CL>, &qc) == cudaSuccess && nc > 0 && nc < max_clusters)
+        max_clusters = nc;
+      else
+        (void)cudaGetLastError();
+    }
+  }
+  const uint32_t workers = (uint32_t)max_clusters;
   const uint32_t nw = (uint32_t)(total < workers ? total : workers);
   dd.total_tiles = (uint32_t)total;
   dd.tiles_per_cta = (uint32_t)((total + nw - 1) / nw);
   const uint32_t used = (uint32_t)((total + dd.tiles_per_cta - 1) / dd.tiles_per_cta);
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(PAIR ? 2 * used : used);
+  cfg.gridDim = dim3(CL * used);
   cfg.blockDim = dim3(NUM_THREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = PAIR ? 2 : 1;
+  attr[0].val.clusterDim.x = CL;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, mtgemm_kernel<BN, PAIR>, tmA, tmB, tmO64, tmO32, tmR64, tmR32, dd);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, mtgemm_kernel<BN, CL>, tmA, tmAh, tmB, tmO64, tmO32, tmR64, tmR32, dd);
   if (e != cudaSuccess) return cuda_fail(e, "mtgemm launch");
   return 0;
 }
@@ -626,7 +689,7 @@ static int pair_mode() {
   if (g_pair_mode < 0) {
     const char* e = getenv("B200SVD_PAIR");
     g_pair_mode = e ? atoi(e) : 2;
-    if (g_pair_mode < 0 || g_pair_mode > 2) g_pair_mode = 2;
+    if (g_pair_mode < 0 || g_pair_mode > 3) g_pair_mode = 2;
   }
   return g_pair_mode;
 }
@@ -635,7 +698,7 @@ static int pair_mode() {
 
 extern "C" int b200svd_gemm_pair_mode(int mode) {
   const int prev = b200::pair_mode();
-  if (mode >= 0 && mode <= 2) b200::g_pair_mode = mode;
+  if (mode >= 0 && mode <= 3) b200::g_pair_mode = mode;
   return prev;
 }
 
@@ -724,8 +787,9 @@ extern "C" int b200svd_gemm(const b200svd_gemm_params* p, void* stream) {
     if (p->n <= 32) bn = 32;
     else if (p->n <= 64) bn = 64;
     else if (p->n <= 128) bn = 128;
-    else if (p->n % 256 == 0) bn = 256;
-    else if (p->n % 160 == 0) bn = 160;
+    // the pair tiles are bound by L2->SM bytes per FLOP (tools/bench_bn.py): the 256-wide tile wins even with a
+    // ragged last tile (its out-of-range weight rows are TMA zero fill, not traffic); N = 160 / 320 fit the 160 tile
+    else if (p->n == 160 || p->n == 320) bn = 160;
     else bn = 256;
   }
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
@@ -745,14 +809,21 @@ extern "C" int b200svd_gemm(const b200svd_gemm_params* p, void* stream) {
   // 2-SM (cta_group::2) tiles whenever a wide tile has at least two M tiles: measured neutral-to-better on every
   // shape of the denoiser (profiles/r01_pair_shapes.txt); mode 1 additionally pairs the 128-wide tile
   const uint64_t m_tiles_all = (uint64_t)d.m_tiles[0] * d.m_tiles[1] * d.m_tiles[2];
+  // a single M tile cannot pair: the 128-wide tile spreads such a (weight-streaming) GEMM over more SMs
+  if (p->bn == 0 && bn == 256 && m_tiles_all < 2 && p->act != B200SVD_ACT_GEGLU) bn = 128;
   const int pm = pair_mode();
   const bool pair = m_tiles_all >= 2 && ((pm >= 1 && (bn == 256 || bn == 160)) || (pm == 1 && bn == 128));
+  // mode 3: two pairs on adjacent N tiles share (multicast) their A tile when the N tile count is even
+  const uint32_t n_tiles_all = (p->n + (uint32_t)bn - 1) / (uint32_t)bn;
+  const bool quad = pair && pm == 3 && (n_tiles_all % 2) == 0;
   switch (bn) {
-    case 32: return launch<32, false>(p, tmA, d, st);
-    case 64: return launch<64, false>(p, tmA, d, st);
-    case 128: return pair ? launch<128, true>(p, tmA, d, st) : launch<128, false>(p, tmA, d, st);
-    case 160: return pair ? launch<160, true>(p, tmA, d, st) : launch<160, false>(p, tmA, d, st);
-    case 256: return pair ? launch<256, true>(p, tmA, d, st) : launch<256, false>(p, tmA, d, st);
+    case 32: return launch<32, 1>(p, tmA, d, st);
+    case 64: return launch<64, 1>(p, tmA, d, st);
+    case 128: return pair ? launch<128, 2>(p, tmA, d, st) : launch<128, 1>(p, tmA, d, st);
+    case 160:
+      return quad ? launch<160, 4>(p, tmA, d, st) : pair ? launch<160, 2>(p, tmA, d, st) : launch<160, 1>(p, tmA, d, st);
+    case 256:
+      return quad ? launch<256, 4>(p, tmA, d, st) : pair ? launch<256, 2>(p, tmA, d, st) : launch<256, 1>(p, tmA, d, st);
     default: set_error("b200svd_gemm: unsupported N tile %d", bn); return 1;
   }
 }

@@ -129,18 +129,24 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx
   const int cpg = C >> 5;
   const double cnt = (double)P * (double)cpg;
   float sc[8], sh[8];
+  int gprev = -1;
+  float mean_f = 0.f, rstd = 0.f;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int c = v * 8 + j;
     const int g = c / cpg;
-    const double su = sums[((int64_t)n * 32 + g) * 2], sq = sums[((int64_t)n * 32 + g) * 2 + 1];
-    const double mean = su / cnt;
-    double var = sq / cnt - mean * mean;
-    if (var < 0.0) var = 0.0;
-    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    if (g != gprev) {  // the double-precision statistics are evaluated once per distinct group (<= 2 for C >= 256)
+      const double su = sums[((int64_t)n * 32 + g) * 2], sq = sums[((int64_t)n * 32 + g) * 2 + 1];
+      const double mean = su / cnt;
+      double var = sq / cnt - mean * mean;
+      if (var < 0.0) var = 0.0;
+      rstd = rsqrtf((float)var + eps);
+      mean_f = (float)mean;
+      gprev = g;
+    }
     const float ga = __ldg(gamma + c), be = __ldg(beta + c);
     sc[j] = rstd * ga;
-    sh[j] = be - (float)mean * rstd * ga;
+    sh[j] = be - mean_f * rstd * ga;
   }
   const __nv_bfloat16* xb = x + ((int64_t)n * P) * ldx + v * 8;
   __nv_bfloat16* yb = y + ((int64_t)n * P) * ldy + v * 8;
@@ -152,8 +158,8 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx
       float a = bf16_lo(w[j]) * sc[2 * j] + sh[2 * j];
       float b = bf16_hi(w[j]) * sc[2 * j + 1] + sh[2 * j + 1];
       if (apply_silu) {
-        a = silu_f(a);
-        b = silu_f(b);
+        a = silu_fast(a);
+        b = silu_fast(b);
       }
       o[j] = pack_bf16x2(a, b);
     }
@@ -248,13 +254,70 @@ __global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, int64_t ld
       for (int j = 0; j < 8; ++j) {
         const int c = v * 8 + j;
         float t = (val[i][j] - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c);
-        if (apply_silu) t = silu_f(t);
+        if (apply_silu) t = silu_fast(t);
         o8[j] = t;
       }
       *reinterpret_cast<uint4*>(yr + v * 8) = make_uint4(pack_bf16x2(o8[0], o8[1]), pack_bf16x2(o8[2], o8[3]),
                                                           pack_bf16x2(o8[4], o8[5]), pack_bf16x2(o8[6], o8[7]));
     }
   }
+}
+
+// Narrow rows (C <= 256: the ControlNet condition-embedding norms): LPR lanes own one row, one 16-byte vector each
+// (lanes >= C/8 idle), 32/LPR rows per warp, so a warp issues full-width loads instead of one 64-byte row at a time.
+template <int LPR>
+__global__ void __launch_bounds__(256) layernorm_narrow_kernel(
+    const __nv_bfloat16* __restrict__ x, int64_t ldx, __nv_bfloat16* __restrict__ y, int64_t ldy, int64_t rows, int C,
+    const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int apply_silu) {
+  constexpr int RPW = 32 / LPR;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / LPR, li = lane % LPR;
+  const int64_t row = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + sub;
+  const bool active = row < rows && li < (C >> 3);
+  float val[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) val[j] = 0.f;
+  if (active) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + row * ldx + li * 8));
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      val[2 * j] = bf16_lo(w[j]);
+      val[2 * j + 1] = bf16_hi(w[j]);
+    }
+  }
+  float sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sum += val[j];
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / (float)C;
+  float sq = 0.f;
+  if (active) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float d = val[j] - mean;
+      sq += d * d;
+    }
+  }
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  const float rstd = rsqrtf(sq / (float)C + eps);
+  if (!active) return;
+  const int c0 = li * 8;
+  const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c0)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c0) + 1);
+  const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c0)), b1 = __ldg(reinterpret_cast<const float4*>(beta + c0) + 1);
+  const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+  const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+  float o8[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float t = (val[j] - mean) * rstd * gg[j] + bb[j];
+    if (apply_silu) t = silu_fast(t);
+    o8[j] = t;
+  }
+  *reinterpret_cast<uint4*>(y + row * ldy + c0) = make_uint4(pack_bf16x2(o8[0], o8[1]), pack_bf16x2(o8[2], o8[3]),
+                                                             pack_bf16x2(o8[4], o8[5]), pack_bf16x2(o8[6], o8[7]));
 }
 
 // Fast path for C = 40*LPR channels-vectors (C = 320, 640, 1280): LPR lanes own one row, 5 x 16-byte vectors each,
@@ -337,7 +400,7 @@ __global__ void __launch_bounds__(256) layernorm5_kernel(
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float t = (val[i][j] - mean) * rstd * gg[j] + bb[j];
-      if (apply_silu) t = silu_f(t);
+      if (apply_silu) t = silu_fast(t);
       o8[j] = t;
     }
     *reinterpret_cast<uint4*>(yr + c0) = make_uint4(pack_bf16x2(o8[0], o8[1]), pack_bf16x2(o8[2], o8[3]),
@@ -464,6 +527,21 @@ int b200svd_layernorm(const void* x, int64_t ldx, void* y, int64_t ldy, int64_t 
     else
       layernorm5_kernel<32><<<g5, wpb * 32, 0, st>>>(xp, ldx, yp, ldy, rows, c, gamma, beta, eps, fvec, ldf, rows_per_frame, xs, ldxs, apply_silu);
     B200_CHECK_LAUNCH("layernorm5");
+    return 0;
+  }
+  if (vecs <= 32 && fvec == nullptr && xsum == nullptr && gb_ok) {
+    const int lpr = vecs <= 4 ? 4 : vecs <= 8 ? 8 : vecs <= 16 ? 16 : 32;
+    const int rpw = 32 / lpr;
+    const unsigned gn = (unsigned)((rows + (int64_t)wpb * rpw - 1) / ((int64_t)wpb * rpw));
+    if (lpr == 4)
+      layernorm_narrow_kernel<4><<<gn, wpb * 32, 0, st>>>(xp, ldx, yp, ldy, rows, c, gamma, beta, eps, apply_silu);
+    else if (lpr == 8)
+      layernorm_narrow_kernel<8><<<gn, wpb * 32, 0, st>>>(xp, ldx, yp, ldy, rows, c, gamma, beta, eps, apply_silu);
+    else if (lpr == 16)
+      layernorm_narrow_kernel<16><<<gn, wpb * 32, 0, st>>>(xp, ldx, yp, ldy, rows, c, gamma, beta, eps, apply_silu);
+    else
+      layernorm_narrow_kernel<32><<<gn, wpb * 32, 0, st>>>(xp, ldx, yp, ldy, rows, c, gamma, beta, eps, apply_silu);
+    B200_CHECK_LAUNCH("layernorm_narrow");
     return 0;
   }
 #define LN_LAUNCH(MV)                                                                                              \

@@ -47,6 +47,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// Wait that parks the thread in hardware (suspend-time hint, ns) instead of re-polling every few dozen cycles: for
+// waits that are expected to be long and whose pollers would otherwise take issue slots from working warps.
+__device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}"
+      ::"r"(smem_u32(bar)), "r"(parity), "r"(20000u)
+      : "memory");
+}
 
 // ----------------------------------------------------------------------------------------------
 // TMA tiled loads (global -> shared, completion on an mbarrier)
@@ -247,11 +260,22 @@ __device__ __forceinline__ void umma_f16_ss_2sm(uint32_t tmem_d, uint64_t adesc,
       : "memory");
 }
 // commit -> arrive on the mbarrier at this offset in BOTH CTAs of the pair
-__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar, uint16_t cta_mask = 3) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
                    smem_u32(bar)),
-               "h"((uint16_t)3)
+               "h"(cta_mask)
                : "memory");
+}
+// 2-SM tiled load multicast to the CTAs of cta_mask (same smem offset in each); every destination's bytes are
+// credited to the barrier of the leader of ITS pair
+__device__ __forceinline__ void tma_load_5d_2sm_mc(void* smem, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                                   int c2, int c3, int c4, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], "
+      "[%1, {%4, %5, %6, %7, %8}], [%2], %3;" ::"r"(smem_u32(smem)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerBitMask), "h"(cta_mask), "r"(c0), "r"(c1), "r"(c2),
+      "r"(c3), "r"(c4)
+      : "memory");
 }
 // arrive on the leader CTA's mbarrier (from either CTA of the pair)
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
@@ -300,6 +324,18 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// 2^x on the FMA/ALU pipes (no MUFU): round-to-nearest split x = n + f, |f| <= 0.5, cubic for 2^f (rel err < 7e-4,
+// below the bf16 rounding the attention probabilities get anyway), exponent patched in with one integer add.
+// Valid for x <= 127; x below -126 is clamped (result ~1e-38).
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -126.0f);
+  const float t = x + 12582912.0f;  // 1.5 * 2^23: the low mantissa bits now hold round(x)
+  const float f = x - (t - 12582912.0f);
+  float pl = fmaf(0.0555041f, f, 0.2402265f);
+  pl = fmaf(pl, f, 0.6931472f);
+  pl = fmaf(pl, f, 1.0f);
+  return __uint_as_float(__float_as_uint(pl) + (__float_as_uint(t) << 23));
+}
 __device__ __forceinline__ float rcp_approx(float x) {
   float y;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -308,20 +344,19 @@ __device__ __forceinline__ float rcp_approx(float x) {
 __device__ __forceinline__ float gelu_f(float x) {  // exact (erf) GELU, matches torch F.gelu default
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
 }
-// erf via Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, far below the bf16 output rounding): 2 MUFU + ~10 FMA,
-// branch free.  Used in the GEGLU epilogue where erff's ~35 instructions made the epilogue ALU-bound.
+// GELU(x) = x * Phi(x) with erf via Abramowitz-Stegun 7.1.25 (|abs err| <= 2.5e-5, two orders below the bf16 output
+// rounding): 2 MUFU + 10 FMA-pipe instructions, branch free.  erff's ~35 instructions made the GEGLU epilogue
+// issue-bound (profiles/r01_ncu_v4_geglu_details.txt).
+//   gelu = h + |h| * erf(|x|/sqrt2),  h = x/2;  erf(z) = 1 - (a1 t + a2 t^2 + a3 t^3) exp(-z^2),  t = 1/(1 + p z)
 __device__ __forceinline__ float gelu_fast(float x) {
-  const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = rcp_approx(fmaf(0.3275911f, z, 1.0f));
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
+  const float t = rcp_approx(fmaf(0.47047f * 0.70710678118654752440f, fabsf(x), 1.0f));
+  float poly = fmaf(0.7478556f, t, -0.0958798f);
+  poly = fmaf(poly, t, 0.3480242f);
   poly *= t;
-  const float e = ex2_approx(-z * z * 1.4426950408889634f);
-  const float erf_abs = fmaf(-poly, e, 1.0f);          // erf(|x|/sqrt2)
-  const float erfv = copysignf(erf_abs, x);
-  return 0.5f * x * (1.0f + erfv);
+  const float e = ex2_approx((x * x) * (-0.5f * 1.4426950408889634f));  // exp(-x^2/2)
+  const float h = 0.5f * x;
+  const float pe = poly * e;
+  return fmaf(-fabsf(h), pe, h + fabsf(h));
 }
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);

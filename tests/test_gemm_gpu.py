@@ -9,9 +9,10 @@ import torch.nn.functional as F
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(autouse=True, params=[0, 1], ids=["1sm", "2sm"])
+@pytest.fixture(autouse=True, params=[0, 1, 3], ids=["1sm", "2sm", "4cl"])
 def pair_mode(request, cuda_dev):
-    """Every case runs with the single-CTA tiles only and with the CTA-pair (cta_group::2) tiles forced on."""
+    """Every case runs with the single-CTA tiles only, with the CTA-pair (cta_group::2) tiles forced on, and with
+    clusters of two pairs sharing their A tile by TMA multicast (where the N tile count is even)."""
     from streamingt2v_b200 import ops
     prev = ops.gemm_pair_mode(request.param)
     yield request.param
