@@ -153,6 +153,20 @@ int b200svd_transpose(const void* in, int64_t ldi, void* out, int64_t ldo, int r
 int b200svd_apm_mix(const float* ctx, int n, int l, int d, const float* w, const float* wb, const float* ln_g,
                     const float* ln_b, const float* alpha, void* out, void* stream);
 
+/* ---- sampler arithmetic around the seam (fp32, NCHW latents) -----------------
+ * The reference has no FFI here; these replace the per-step elementwise torch ops of
+ *   Denoiser.forward + VScalingWithEDMcNoise   sgm/modules/diffusionmodules/denoiser.py:23-39, denoiser_scaling.py:51-59
+ *   LinearPredictionGuider                     .../guiders.py:60-99 (doubled batch: rows [0,rows) unconditional,
+ *                                              [rows,2*rows) conditional)
+ *   EulerEDMSampler.sampler_step (gamma = 0)   .../sampling.py:82-103,211-215
+ * prepare: xin2[2*rows*chw] = cat([x, x]) * c_in.
+ * step:    x_next = x + (next_sigma - sigma) * (x - denoised) / sigma with
+ *          denoised = D_u + scale[t] * (D_c - D_u), D_* = net_* * c_out + x * c_skip, t = row % num_frames;
+ *          scale = num_frames device floats (torch.linspace(min_scale, max_scale, num_frames)). */
+int b200svd_sampler_prepare(const float* x, float* xin2, int64_t rows, int64_t chw, float c_in, void* stream);
+int b200svd_sampler_step(const float* net, const float* x, float* x_next, int64_t rows, int64_t chw, int num_frames,
+                         const float* scale, float c_skip, float c_out, float sigma, float next_sigma, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

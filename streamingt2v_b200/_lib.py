@@ -104,6 +104,8 @@ PROTOTYPES = {
     "b200svd_softmax_rows": [_P, _I64, _P, _I64, _I64, _I, _P],
     "b200svd_transpose": [_P, _I64, _P, _I64, _I, _I, _P],
     "b200svd_apm_mix": [_P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P],
+    "b200svd_sampler_prepare": [_P, _P, _I64, _I64, _F, _P],
+    "b200svd_sampler_step": [_P, _P, _P, _I64, _I64, _I, _P, _F, _F, _F, _F, _P],
 }
 
 

@@ -152,6 +152,34 @@ __global__ void apm_mix_kernel(const float* __restrict__ ctx, int L, int D, cons
 
 static inline unsigned blocks_for(int64_t total, int threads) { return (unsigned)((total + threads - 1) / threads); }
 
+
+// Sampler arithmetic around the denoiser seam (fp32, elementwise).
+// prepare: xin2 = cat([x, x]) * c_in            (guiders.py:97 doubled batch, denoiser.py:36 input scaling)
+__global__ void sampler_prepare_kernel(const float* __restrict__ x, float* __restrict__ xin2, int64_t n, float c_in) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = __ldg(x + i) * c_in;
+  xin2[i] = v;
+  xin2[n + i] = v;
+}
+// step: denoised = c_skip*x + c_out*(net_u + s_t*(net_c - net_u))   (denoiser.py:33-39 + guiders.py:78-86; both
+//       halves of the doubled batch carry the same x); d = (x - denoised)/sigma; x_next = x + (sigma_next - sigma)*d
+//       (sampling.py:100-103, 213-215).  Evaluated in the reference's operation order so that fp32 rounding matches.
+__global__ void sampler_step_kernel(const float* __restrict__ net, const float* __restrict__ x,
+                                    float* __restrict__ x_next, int64_t n, int64_t chw, int num_frames,
+                                    const float* __restrict__ scale, float c_skip, float c_out, float sigma,
+                                    float next_sigma) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float xv = __ldg(x + i);
+  const float s = __ldg(scale + (int)((i / chw) % num_frames));
+  const float du = __ldg(net + i) * c_out + xv * c_skip;
+  const float dc = __ldg(net + n + i) * c_out + xv * c_skip;
+  const float den = du + s * (dc - du);
+  const float d = (xv - den) / sigma;
+  x_next[i] = xv + (next_sigma - sigma) * d;
+}
+
 }  // namespace b200
 
 extern "C" {
@@ -342,6 +370,35 @@ int b200svd_transpose(const void* in, int64_t ldi, void* out, int64_t ldo, int r
   transpose_kernel<<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(in), ldi, reinterpret_cast<__nv_bfloat16*>(out), ldo, rows, cols);
   B200_CHECK_LAUNCH("transpose");
+  return 0;
+}
+
+int b200svd_sampler_prepare(const float* x, float* xin2, int64_t rows, int64_t chw, float c_in, void* stream) {
+  using namespace b200;
+  const int64_t n = rows * chw;
+  if (n <= 0) return 0;
+  sampler_prepare_kernel<<<(unsigned)((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, xin2, n,
+                                                                                                         c_in);
+  B200_CHECK_LAUNCH("sampler_prepare");
+  return 0;
+}
+
+int b200svd_sampler_step(const float* net, const float* x, float* x_next, int64_t rows, int64_t chw, int num_frames,
+                         const float* scale, float c_skip, float c_out, float sigma, float next_sigma, void* stream) {
+  using namespace b200;
+  if (num_frames < 1 || rows % num_frames != 0) {
+    set_error("sampler_step: rows (%lld) must be a multiple of num_frames (%d)", (long long)rows, num_frames);
+    return 1;
+  }
+  if (!(sigma > 0.f)) {
+    set_error("sampler_step: sigma must be positive");
+    return 1;
+  }
+  const int64_t n = rows * chw;
+  if (n <= 0) return 0;
+  sampler_step_kernel<<<(unsigned)((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      net, x, x_next, n, chw, num_frames, scale, c_skip, c_out, sigma, next_sigma);
+  B200_CHECK_LAUNCH("sampler_step");
   return 0;
 }
 

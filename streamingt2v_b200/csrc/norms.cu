@@ -101,19 +101,25 @@ __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx
     double* dsm = reinterpret_cast<double*>(sm);  // reuse the staging area: needs parts*64 doubles <= 2*C*rstep floats
     const int pr = threadIdx.x % pairs, part = threadIdx.x / pairs;
     if (part < parts) {
-      // eight independent partial sums keep eight loads in flight (the chain of dependent double adds over up to
-      // ~1000 chunk partials used to dominate the launch for few, large samples); the order stays fixed
+      // 16 independent partial sums keep 16 loads in flight per thread (the chain of dependent double adds over up
+      // to ~1000 chunk partials, one L2 round trip each, used to dominate the launch for few, large samples); the
+      // summation order stays fixed
       const double* src = partial + (int64_t)n * chunks * 64 + (pr & 31) * 2 + (pr >> 5);
-      double a[8];
+      constexpr int W = 16;
+      double a[W];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) a[i] = 0.0;
+      for (int i = 0; i < W; ++i) a[i] = 0.0;
       int c = part;
-      for (; c + 7 * parts < chunks; c += 8 * parts) {
+      for (; c + (W - 1) * parts < chunks; c += W * parts) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) a[i] += src[(int64_t)(c + i * parts) * 64];
+        for (int i = 0; i < W; ++i) a[i] += src[(int64_t)(c + i * parts) * 64];
       }
       for (; c < chunks; c += parts) a[0] += src[(int64_t)c * 64];
-      dsm[part * pairs + pr] = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+#pragma unroll
+      for (int w = W / 2; w > 0; w >>= 1)
+#pragma unroll
+        for (int i = 0; i < w; ++i) a[i] += a[i + w];
+      dsm[part * pairs + pr] = a[0];
     }
     __syncthreads();
     if (threadIdx.x < pairs) {

@@ -455,6 +455,34 @@ def transpose(x):
     return out
 
 
+def sampler_prepare(x, c_in, out=None):
+    """cat([x, x]) * c_in: the doubled, input-scaled latent the denoiser network sees (guiders.py:97,
+    denoiser.py:36).  x: contiguous fp32 [(b t), ...] -> [2 (b t), ...]."""
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    rows = x.shape[0]
+    chw = x.numel() // max(rows, 1)
+    if out is None:
+        out = torch.empty((2 * rows,) + tuple(x.shape[1:]), dtype=torch.float32, device=x.device)
+    assert out.dtype == torch.float32 and out.is_contiguous() and out.numel() == 2 * x.numel()
+    _call("b200svd_sampler_prepare", _ptr(x), _ptr(out), rows, chw, float(c_in), _stream(), nbytes=12.0 * x.numel())
+    return out
+
+
+def sampler_step(net, x, scale, *, num_frames, c_skip, c_out, sigma, next_sigma, out=None):
+    """Denoiser output scaling + LinearPredictionGuider + Euler update in one kernel (denoiser.py:33-39,
+    guiders.py:78-86, sampling.py:100-103).  net: fp32 [2 (b t), ...] (unconditional half first), x: fp32
+    [(b t), ...], scale: fp32 [num_frames] on the device."""
+    assert net.dtype == torch.float32 and net.is_contiguous() and x.dtype == torch.float32 and x.is_contiguous()
+    assert net.numel() == 2 * x.numel() and scale.dtype == torch.float32 and scale.numel() == num_frames
+    rows = x.shape[0]
+    chw = x.numel() // max(rows, 1)
+    if out is None:
+        out = torch.empty_like(x)
+    _call("b200svd_sampler_step", _ptr(net), _ptr(x), _ptr(out), rows, chw, int(num_frames), _ptr(scale),
+          float(c_skip), float(c_out), float(sigma), float(next_sigma), _stream(), nbytes=16.0 * x.numel())
+    return out
+
+
 def attention_single_head(q, k, v, n, s):
     """softmax(q k^T / sqrt(C)) v per frame, one head of width C (VAE AttnBlock).  q, k, v: contiguous [(n s), C] bf16.
     Built from the tensor-core GEMM (scores in fp32), a row-softmax kernel and a transpose."""

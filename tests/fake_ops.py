@@ -225,6 +225,30 @@ def transpose(x):
     return x.t().contiguous()
 
 
+def sampler_prepare(x, c_in, out=None):
+    _count()
+    v = torch.cat([x, x], 0) * c_in
+    if out is not None:
+        out.copy_(v)
+        return out
+    return v
+
+
+def sampler_step(net, x, scale, *, num_frames, c_skip, c_out, sigma, next_sigma, out=None):
+    _count()
+    ex = (slice(None),) + (None,) * (x.dim() - 1)
+    xx = torch.cat([x, x], 0)
+    den = net * c_out + xx * c_skip
+    d_u, d_c = den.chunk(2)
+    s = scale.repeat(x.shape[0] // num_frames)[ex]
+    den = d_u + s * (d_c - d_u)
+    r = x + (next_sigma - sigma) * ((x - den) / sigma)
+    if out is not None:
+        out.copy_(r)
+        return out
+    return r
+
+
 def attention_single_head(q, k, v, n, s):
     Cc = q.shape[1]
     out = torch.empty((n * s, Cc), dtype=torch.bfloat16)
