@@ -26,12 +26,11 @@ _GUIDED_KEYS = ("vector", "crossattn", "concat")  # guiders.py:91
 
 class B200EulerEDMSampler:
     def __init__(self, num_steps: int = 30, num_frames: int = 25, min_scale: float = 1.5, max_scale: float = 3.0,
-                 additional_cond_keys=(), ops_module=None):
+                 additional_cond_keys=()):
         self.num_steps = int(num_steps)
         self.num_frames = int(num_frames)
         self.min_scale, self.max_scale = float(min_scale), float(max_scale)
         self.additional_cond_keys = tuple(additional_cond_keys)
-        self._ops = ops_module if ops_module is not None else ops   # tests inject a CPU stand-in for the host logic
         self._scale = None
 
     # -- AlignYourSteps.get_sigmas + Discretization.__call__(do_append_zero=True) ---------------------------------
@@ -68,10 +67,10 @@ class B200EulerEDMSampler:
     # -- EDMSampler.sampler_step with gamma = 0 (sampling.py:82-103) ----------------------------------------------
     def sampler_step(self, network, x, sigma: float, next_sigma: float, cond2: dict, **kw):
         c_skip, c_out, c_in, c_noise = self.scalings(float(sigma))
-        xin = self._ops.sampler_prepare(x, c_in)
+        xin = ops.sampler_prepare(x, c_in)
         t = torch.full((xin.shape[0],), c_noise, dtype=torch.float32, device=x.device)
         net = network(xin, t, cond2, **kw)
-        return self._ops.sampler_step(net.contiguous(), x, self._guider_scale(x.device), num_frames=self.num_frames,
+        return ops.sampler_step(net.contiguous(), x, self._guider_scale(x.device), num_frames=self.num_frames,
                                       c_skip=c_skip, c_out=c_out, sigma=float(sigma), next_sigma=float(next_sigma))
 
     # -- EDMSampler.__call__ (sampling.py:105-127; prepare_sampling_loop :42-58) ----------------------------------
@@ -79,7 +78,7 @@ class B200EulerEDMSampler:
         sigmas = self.get_sigmas(num_steps)
         cond2 = self.prepare_cond(cond, cond if uc is None else uc)
         # x *= sqrt(1 + sigma_0^2) (sampling.py:47): the first half of the doubling kernel's output
-        x = self._ops.sampler_prepare(x.to(torch.float32).contiguous(), math.sqrt(1.0 + float(sigmas[0]) ** 2))[:x.shape[0]]
+        x = ops.sampler_prepare(x.to(torch.float32).contiguous(), math.sqrt(1.0 + float(sigmas[0]) ** 2))[:x.shape[0]]
         for i in range(len(sigmas) - 1):
             x = self.sampler_step(network, x, float(sigmas[i]), float(sigmas[i + 1]), cond2, **kw)
         return x

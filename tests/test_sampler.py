@@ -57,15 +57,17 @@ def _oracle_loop(x, cond, uc, num_steps, T):
     return x
 
 
-def test_host_sampler_loop_matches_oracle_cpu():
-    from streamingt2v_b200.sampler import B200EulerEDMSampler
+def test_host_sampler_loop_matches_oracle_cpu(monkeypatch):
     import fake_ops
+    from streamingt2v_b200 import sampler as sampler_mod
+    from streamingt2v_b200.sampler import B200EulerEDMSampler
+    monkeypatch.setattr(sampler_mod, "ops", fake_ops)   # host logic only: CPU stand-in for the two CUDA kernels
     T = 5
     g = torch.Generator().manual_seed(0)
     x = torch.randn(2 * T, 4, 6, 8, generator=g)      # b = 2 videos of T frames
     cond = {"vector": torch.randn(2 * T, 3, generator=g), "flag": 7}
     uc = {"vector": torch.zeros(2 * T, 3), "flag": 7}
-    smp = B200EulerEDMSampler(num_steps=6, num_frames=T, ops_module=fake_ops)
+    smp = B200EulerEDMSampler(num_steps=6, num_frames=T)
     out = smp(_fake_network(3), x.clone(), cond, uc)
     ref = _oracle_loop(x.clone(), cond, uc, 6, T)
     assert out.shape == x.shape
