@@ -31,6 +31,9 @@ CASES = {
     "tiny_t8_16x16": (arch.TINY, 8, 16, 16, 1, 1),
     "tiny_t25_8x16": (arch.TINY, 25, 8, 16, 1, 2),
     "tiny_apm_t8_16x16": (dataclasses.replace(arch.TINY, use_apm=True), 8, 16, 16, 17, 3),
+    # extents that are not powers of two on every level (24x40 -> 12x20 -> 6x10 -> 3x5), like the production
+    # 72x128 -> 9x16: ragged 128-row tiles and TMA boxes larger than the tensor
+    "tiny_t7_24x40": (arch.TINY, 7, 24, 40, 1, 4),
 }
 
 

@@ -21,7 +21,7 @@ def _rel(a, b):
     return ((a - b).norm() / b.norm()).item()
 
 
-CASES = [("tiny_t8_16x16", False), ("tiny_t25_8x16", False), ("tiny_apm_t8_16x16", True)]
+CASES = [("tiny_t8_16x16", False), ("tiny_t25_8x16", False), ("tiny_apm_t8_16x16", True), ("tiny_t7_24x40", False)]
 
 
 @pytest.mark.parametrize("name,apm", CASES)

@@ -10,7 +10,7 @@ import torch
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 
 
-@pytest.mark.parametrize("name", ["tiny_t8_16x16", "tiny_apm_t8_16x16", "tiny_t25_8x16"])
+@pytest.mark.parametrize("name", ["tiny_t8_16x16", "tiny_apm_t8_16x16", "tiny_t25_8x16", "tiny_t7_24x40"])
 def test_oracle_matches_reference_golden(name):
     from oracle import streaming_svd_oracle as orc
     from streamingt2v_b200 import arch, synth
