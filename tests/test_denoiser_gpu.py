@@ -86,3 +86,38 @@ def test_no_controlnet_path(cuda_dev):
     r = _rel(out, ref)
     print(f"no-controlnet: rel_l2={r:.4e}")
     assert r < REL_TOL
+
+
+def test_full_size_properties(cuda_dev):
+    """BASELINE.json's full configuration (25 frames, 72x128 latent, CFG batch 2, full-width network), where the
+    oracle is too slow to be the checker: size-independent properties of the seam instead.
+      * finite and bit-for-bit deterministic;
+      * the two videos of the batch never interact (every op on the path is per frame, per (video, pixel) or per
+        video): changing video 1's inputs leaves video 0's output bit-identical and changes video 1's."""
+    from streamingt2v_b200 import arch, synth
+    from streamingt2v_b200.model import B200Denoiser
+    cfg = arch.UNetConfig()
+    T, h, w = 25, 72, 128
+    eng = B200Denoiser(cfg, arch.synth_state_dict_device(arch.unet_param_shapes(cfg), cuda_dev, 1),
+                       arch.synth_state_dict_device(arch.controlnet_param_shapes(cfg), cuda_dev, 2), cuda_dev)
+    x, t, c, kw = synth.make_inputs(cfg, T=T, h=h, w=w, seed=5)
+    x, t = x.to(cuda_dev), t.to(cuda_dev)
+    c = {k: v.to(cuda_dev) for k, v in c.items()}
+    ctrl = kw["ctrl_frames"].to(cuda_dev)
+
+    def run():
+        o = eng.forward(x, t, c, batch_size=2, num_video_frames=T, ctrl_frames=ctrl)
+        torch.cuda.synchronize()
+        return o.float().clone()
+
+    o1 = run()
+    assert o1.shape == (2 * T, 4, h, w) and bool(torch.isfinite(o1).all())
+    assert float(o1.std()) > 0.0
+    assert torch.equal(o1, run()), "full-size forward is not deterministic"
+    x[T:].mul_(-0.5)                      # video 1 only (in place: the conditioning cache keys on tensor versions)
+    c["concat"][T:].add_(0.25)
+    c["crossattn"][T:].mul_(1.5)
+    c["vector"][T:].mul_(-1.0)
+    o3 = run()
+    assert torch.equal(o3[:T], o1[:T]), "video 0 changed when only video 1's inputs changed"
+    assert not torch.equal(o3[T:], o1[T:])
