@@ -25,7 +25,7 @@ from typing import Dict, List, Optional
 import torch
 import torch.nn.functional as F
 
-from streamingt2v_b200.arch import Attn, Down, Plan, Res, Up, UNetConfig, build_plan
+from streamingt2v_b200.arch import Attn, Down, Res, Up, UNetConfig, build_plan
 
 SD = Dict[str, torch.Tensor]
 

@@ -10,7 +10,7 @@ with the reference's own `state_dict()` (pinned by oracle/make_golden.py) would 
 from __future__ import annotations
 
 from dataclasses import dataclass, field
-from typing import Dict, List, Optional, Tuple
+from typing import Dict, List, Tuple
 
 
 @dataclass(frozen=True)

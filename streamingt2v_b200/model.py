@@ -16,14 +16,13 @@ Every tensor op below is a kernel launch through streamingt2v_b200.ops (C ABI); 
 from __future__ import annotations
 
 import dataclasses
-import math
 from typing import Dict, List, Optional
 
 import torch
 
 from . import ops, packing
 from .arch import Attn, Down, Plan, Res, Up, UNetConfig, build_plan
-from .ops import ACT_GEGLU, ACT_NONE, ACT_SILU
+from .ops import ACT_GEGLU, ACT_SILU
 
 SD = Dict[str, torch.Tensor]
 

@@ -1,7 +1,6 @@
 """CPU: architecture plan, tile picker, weight packing and the distributed helpers (gloo, world_size 2)."""
 import os
 
-import pytest
 import torch
 
 
