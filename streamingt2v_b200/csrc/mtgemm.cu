@@ -641,8 +641,7 @@ static int launch(const b200svd_gemm_params* p, const CUtensorMap& tmA, const Ge
   if (max_clusters == 0) {
     max_clusters = sm_count() / CL;
     if (CL > 1) {
-      cudaLaunchConfig_t qc;
-      memset(&qc, 0, sizeof(qc));
+      cudaLaunchConfig_t qc = {};
       qc.gridDim = dim3((unsigned)(sm_count() / CL * CL));
       qc.blockDim = dim3(NUM_THREADS);
       qc.dynamicSmemBytes = Cfg::SMEM_BYTES;
@@ -665,8 +664,7 @@ static int launch(const b200svd_gemm_params* p, const CUtensorMap& tmA, const Ge
   dd.total_tiles = (uint32_t)total;
   dd.tiles_per_cta = (uint32_t)((total + nw - 1) / nw);
   const uint32_t used = (uint32_t)((total + dd.tiles_per_cta - 1) / dd.tiles_per_cta);
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
+  cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(CL * used);
   cfg.blockDim = dim3(NUM_THREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
