@@ -1,7 +1,9 @@
 """torch.distributed plumbing for the one-process-per-GPU launch (bench.py --gpus N).
 
-The denoiser step does not shard in round 1 ("replicas only"): ranks run independent replicas, and the
-only cross-rank traffic is the timing reduction.  Backend nccl on GPUs, gloo in the CPU tests.
+The throughput benchmark runs independent replicas ("replicas only"): the only cross-rank
+traffic is the timing reduction.  Two opt-in latency modes use the partitions SURVEY.md section 8(e) names — the
+classifier-free-guidance halves of a denoise step (2 ranks, one all-gather of the network output per step) and the
+groups of <= 8 frames of the VAE decode — through `all_gather_cat`.  Backend nccl on GPUs, gloo in the CPU tests.
 """
 from __future__ import annotations
 
@@ -22,6 +24,21 @@ def max_over_ranks(values: Sequence[float], device="cpu") -> List[float]:
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return t.tolist()
+
+
+def all_gather_cat(t: torch.Tensor) -> torch.Tensor:
+    """Concatenate every rank's (equal-shape) tensor along dim 0 in rank order; identity without a process group."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return t
+    parts = [torch.empty_like(t) for _ in range(dist.get_world_size())]
+    dist.all_gather(parts, t.contiguous())
+    return torch.cat(parts, 0)
+
+
+def rank_world():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
 
 
 def shard_items(n_items: int, rank: int, world: int) -> range:

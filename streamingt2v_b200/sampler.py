@@ -17,7 +17,7 @@ import math
 import numpy as np
 import torch
 
-from . import ops
+from . import dist_utils, ops
 
 # models/diffusion/discretizer.py:29-30
 AYS_SCHEDULE = (700.00, 54.5, 15.886, 7.977, 4.248, 1.789, 0.981, 0.403, 0.173, 0.034, 0.002)
@@ -26,11 +26,14 @@ _GUIDED_KEYS = ("vector", "crossattn", "concat")  # guiders.py:91
 
 class B200EulerEDMSampler:
     def __init__(self, num_steps: int = 30, num_frames: int = 25, min_scale: float = 1.5, max_scale: float = 3.0,
-                 additional_cond_keys=()):
+                 additional_cond_keys=(), cfg_parallel: bool = False):
         self.num_steps = int(num_steps)
         self.num_frames = int(num_frames)
         self.min_scale, self.max_scale = float(min_scale), float(max_scale)
         self.additional_cond_keys = tuple(additional_cond_keys)
+        # opt-in 2-rank latency mode: rank 0 evaluates the unconditional half of the doubled
+        # batch, rank 1 the conditional half; one all-gather of the network output [(b t),4,h,w] per step
+        self.cfg_parallel = bool(cfg_parallel)
         self._scale = None
 
     # -- AlignYourSteps.get_sigmas + Discretization.__call__(do_append_zero=True) ---------------------------------
@@ -59,6 +62,24 @@ class B200EulerEDMSampler:
                 out[k] = cond[k]
         return out
 
+    def _my_half(self, cond2: dict, kw: dict):
+        """This rank's half of the doubled conditioning and of the per-batch keyword arguments."""
+        rank, world = dist_utils.rank_world()
+        if world != 2:
+            raise RuntimeError(f"cfg_parallel needs exactly 2 ranks (one per guidance half), got {world}")
+
+        def half(v):
+            n = v.shape[0] // 2
+            return v[rank * n:(rank + 1) * n]
+
+        c = {k: (half(v) if k in _GUIDED_KEYS + self.additional_cond_keys else v) for k, v in cond2.items()}
+        kw = dict(kw)
+        if "batch_size" in kw:
+            kw["batch_size"] = kw["batch_size"] // 2
+        if kw.get("image_only_indicator") is not None:
+            kw["image_only_indicator"] = half(kw["image_only_indicator"])
+        return c, kw
+
     def _guider_scale(self, device):
         if self._scale is None or self._scale.device != torch.device(device):
             self._scale = torch.linspace(self.min_scale, self.max_scale, self.num_frames).to(device)  # guiders.py:71
@@ -68,8 +89,14 @@ class B200EulerEDMSampler:
     def sampler_step(self, network, x, sigma: float, next_sigma: float, cond2: dict, **kw):
         c_skip, c_out, c_in, c_noise = self.scalings(float(sigma))
         xin = ops.sampler_prepare(x, c_in)
+        if self.cfg_parallel:
+            rank, _ = dist_utils.rank_world()
+            bt = x.shape[0]
+            xin = xin[rank * bt:(rank + 1) * bt]          # both halves of the doubled input are identical
         t = torch.full((xin.shape[0],), c_noise, dtype=torch.float32, device=x.device)
         net = network(xin, t, cond2, **kw)
+        if self.cfg_parallel:
+            net = dist_utils.all_gather_cat(net.contiguous())   # rank order == (unconditional, conditional)
         return ops.sampler_step(net.contiguous(), x, self._guider_scale(x.device), num_frames=self.num_frames,
                                       c_skip=c_skip, c_out=c_out, sigma=float(sigma), next_sigma=float(next_sigma))
 
@@ -77,6 +104,8 @@ class B200EulerEDMSampler:
     def __call__(self, network, x, cond, uc=None, num_steps=None, **kw):
         sigmas = self.get_sigmas(num_steps)
         cond2 = self.prepare_cond(cond, cond if uc is None else uc)
+        if self.cfg_parallel:
+            cond2, kw = self._my_half(cond2, kw)
         # x *= sqrt(1 + sigma_0^2) (sampling.py:47): the first half of the doubling kernel's output
         x = ops.sampler_prepare(x.to(torch.float32).contiguous(), math.sqrt(1.0 + float(sigmas[0]) ** 2))[:x.shape[0]]
         for i in range(len(sigmas) - 1):

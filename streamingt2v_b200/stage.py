@@ -22,6 +22,8 @@ from typing import Callable, List, Optional, Sequence, Union
 
 import torch
 
+from . import dist_utils
+
 SCALE_FACTOR = 0.18215      # config.yaml scale_factor (diff_trainer_params.scale_factor)
 MAX_DECODE_CHUNK = 8        # streaming_svd.py:127 (4 with use_memopt)
 SPATIAL_COMPRESSION = 8     # streaming_svd.py:157
@@ -45,7 +47,7 @@ def _to_fchw(video: torch.Tensor) -> torch.Tensor:
 class B200StreamingSVDStage:
     def __init__(self, inference_model, sampler, vae_decoder, conditioner: Callable, *, num_conditional_frames: int = 7,
                  anchor_frame: int = 0, scale_factor: float = SCALE_FACTOR, max_decode_chunk: int = MAX_DECODE_CHUNK,
-                 device="cuda:0"):
+                 device="cuda:0", shard_decode: bool = False):
         self.inference_model = inference_model      # B200StreamingWrapper        (streaming_svd.py:50-56)
         self.sampler = sampler                      # B200EulerEDMSampler         (config.yaml:139-157)
         self.vae_decoder = vae_decoder              # B200VaeDecoder              (first_stage_model.decode)
@@ -55,16 +57,41 @@ class B200StreamingSVDStage:
         self.scale_factor = float(scale_factor)
         self.max_decode_chunk = int(max_decode_chunk)
         self.device = torch.device(device)
+        # opt-in: spread the groups of <= 8 frames of decode_first_stage over the ranks of the process group
+        # ("VAE decode: embarrassingly, frame groups of 8, gather at the end")
+        self.shard_decode = bool(shard_decode)
 
     # -- streaming_svd.py:124-151 ----------------------------------------------------------------------------------
     def decode_first_stage(self, z: torch.Tensor) -> torch.Tensor:
         z = 1.0 / self.scale_factor * z
         n_samples = min(z.shape[0], self.max_decode_chunk)
         n_rounds = math.ceil(z.shape[0] / n_samples)
+        rank, world = dist_utils.rank_world() if self.shard_decode else (0, 1)
+        if world == 1:
+            outs = []
+            for n in range(n_rounds):
+                part = z[n * n_samples:(n + 1) * n_samples]
+                outs.append(self.vae_decoder.decode(part, timesteps=len(part)))
+            return torch.cat(outs, dim=0)
+        # group g is decoded by rank g % world into slot g // world of that rank's contribution
+        slots = math.ceil(n_rounds / world)
+        mine = None
+        for g in range(rank, n_rounds, world):
+            part = z[g * n_samples:(g + 1) * n_samples]
+            out = self.vae_decoder.decode(part, timesteps=len(part))
+            if mine is None:
+                mine = out.new_zeros((slots * n_samples,) + tuple(out.shape[1:]))
+            mine[(g // world) * n_samples:(g // world) * n_samples + len(part)] = out
+        if mine is None:   # more ranks than groups: contribute zeros of the right shape
+            mine = torch.zeros((slots * n_samples, 3, z.shape[-2] * SPATIAL_COMPRESSION,
+                                z.shape[-1] * SPATIAL_COMPRESSION), dtype=torch.float32, device=z.device)
+        allp = dist_utils.all_gather_cat(mine)
+        per_rank = slots * n_samples
         outs = []
-        for n in range(n_rounds):
-            part = z[n * n_samples:(n + 1) * n_samples]
-            outs.append(self.vae_decoder.decode(part, timesteps=len(part)))
+        for g in range(n_rounds):
+            n_g = min(n_samples, z.shape[0] - g * n_samples)
+            o = (g % world) * per_rank + (g // world) * n_samples
+            outs.append(allp[o:o + n_g])
         return torch.cat(outs, dim=0)
 
     # -- streaming_svd.py:263-290 ----------------------------------------------------------------------------------
