@@ -34,7 +34,7 @@ SD = Dict[str, torch.Tensor]
 def timestep_embedding(t: torch.Tensor, dim: int, max_period: float = 10000.0) -> torch.Tensor:
     """diffusionmodules/util.py:207-231 (repeat_only=False)."""
     half = dim // 2
-    freqs = torch.exp(-math.log(max_period) * torch.arange(half, dtype=torch.float32) / half)
+    freqs = torch.exp(-math.log(max_period) * torch.arange(half, dtype=torch.float32, device=t.device) / half)
     args = t[:, None].float() * freqs[None]
     emb = torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
     if dim % 2:
@@ -168,7 +168,7 @@ def spatial_video_transformer(sd: SD, p: str, x: torch.Tensor, context: torch.Te
     x = group_norm(sd, p + ".norm", x, 1e-6)
     x = x.permute(0, 2, 3, 1).reshape(bt, h * w, c)
     x = linear(sd, p + ".proj_in", x)
-    frames = torch.arange(T).repeat(bt // T)
+    frames = torch.arange(T, device=x.device).repeat(bt // T)
     emb = emb_mlp(sd, p + ".time_pos_embed.0", p + ".time_pos_embed.2", timestep_embedding(frames, c))[:, None, :]
     x = basic_transformer_block(sd, p + ".transformer_blocks.0", x, context, heads, use_apm)
     x_mix = video_transformer_block(sd, p + ".time_stack.0", x + emb, time_context, heads, T)

@@ -35,6 +35,14 @@ def all_gather_cat(t: torch.Tensor) -> torch.Tensor:
     return torch.cat(parts, 0)
 
 
+def broadcast_from_rank0(t: torch.Tensor) -> torch.Tensor:
+    """In-place broadcast of rank 0's tensor to every rank (identity without a process group)."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        t = t.contiguous()
+        dist.broadcast(t, src=0)
+    return t
+
+
 def rank_world():
     if dist.is_available() and dist.is_initialized():
         return dist.get_rank(), dist.get_world_size()

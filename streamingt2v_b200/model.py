@@ -16,6 +16,7 @@ Every tensor op below is a kernel launch through streamingt2v_b200.ops (C ABI); 
 from __future__ import annotations
 
 import dataclasses
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -159,6 +160,8 @@ class B200Denoiser:
     def __init__(self, cfg: UNetConfig, sd_unet: SD, sd_ctrl: Optional[SD], device):
         ops._lib.init(torch.device(device).index or 0)
         self.cfg, self.dev = cfg, torch.device(device)
+        if self.dev.type == "cuda" and self.dev.index is None:
+            self.dev = torch.device("cuda", torch.cuda.current_device())
         self.plan_u = build_plan(cfg, "", decoder=True)
         self.wu = _NetWeights(sd_unet, cfg, self.plan_u, self.dev)
         P = packing
@@ -197,8 +200,15 @@ class B200Denoiser:
             )
         self._cond_key = None
         self._cond = None
+        self._cond_refs = None
+        self._cond_epoch = 0      # bumped whenever the conditioning is recomputed
         self._tpe_cache: Dict[tuple, torch.Tensor] = {}
         self.debug_taps: Optional[dict] = None  # name -> bf16 rows tensor (tests only)
+        # CUDA-graph replay of the forward (see _forward_graphed); B200SVD_NO_GRAPH=1 forces eager launches
+        self.use_cuda_graph = self.dev.type == "cuda" and not os.environ.get("B200SVD_NO_GRAPH")
+        self._graphs: Dict[tuple, dict] = {}
+        self._graph_pool = torch.cuda.graph_pool_handle() if self.dev.type == "cuda" else None
+        self._capture_stream = torch.cuda.Stream(self.dev) if self.dev.type == "cuda" else None
 
     # ------------------------------------------------------------------------------------------------------------
     # building blocks
@@ -357,10 +367,14 @@ class B200Denoiser:
 
     def _prepare(self, c, ctrl_frames, B, T, h, w):
         ctx, vec, concat = c["crossattn"], c["vector"], c["concat"]
-        key = tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in (ctx, vec, concat)) + (
-            (ctrl_frames.data_ptr(), ctrl_frames._version, tuple(ctrl_frames.shape)) if ctrl_frames is not None else (),
-            B, T, h, w)
-        if key == self._cond_key:
+        # Cache key = IDENTITY of the conditioning tensors (+ their in-place version counters).  The cache entry
+        # holds strong references to the keyed tensors (self._cond_refs), so their storage cannot be freed and handed
+        # to a new tensor of equal shape while the entry is alive: `is` on a live object is unambiguous, a recycled
+        # data_ptr() is not.
+        keyed = (ctx, vec, concat, ctrl_frames)
+        key = tuple((t._version, tuple(t.shape)) if t is not None else None for t in keyed) + (B, T, h, w)
+        if (self._cond_key == key and self._cond_refs is not None
+                and all(a is b for a, b in zip(self._cond_refs, keyed))):
             return self._cond
         N = B * T
         Fc = self.cfg.num_frame_conditioning
@@ -399,8 +413,13 @@ class B200Denoiser:
             ce = self._cond_embedding(ctrl_frames, h, w)                     # [(Fc S), 320]
             cc["ce"] = ce
             cond["ctrl"] = cc
-        self._cond_key, self._cond = key, cond
+        self._cond_key, self._cond, self._cond_refs = key, cond, keyed
+        self._cond_epoch += 1
         return cond
+
+    def reset_conditioning(self):
+        """Drop the step-invariant conditioning cache (and the references it holds); the next forward recomputes it."""
+        self._cond_key = self._cond = self._cond_refs = None
 
     # ------------------------------------------------------------------------------------------------------------
     # forward
@@ -458,11 +477,67 @@ class B200Denoiser:
         assert N == B * T
         if h % 8 or w % 8:
             raise ValueError("latent height/width must be multiples of 8 (three stride-2 levels)")
+        if self.dev.type == "cuda" and torch.cuda.current_device() != self.dev.index:
+            # launches go to torch's current stream OF THE CURRENT DEVICE: make that this engine's device
+            with torch.cuda.device(self.dev):
+                return self.forward(x, t, c, batch_size=batch_size, num_video_frames=num_video_frames,
+                                    ctrl_frames=ctrl_frames, use_controlnet=use_controlnet)
         dev = self.dev
-        x32 = x.to(dev, torch.float32).contiguous()
-        t32 = t.to(dev, torch.float32).contiguous()
         use_ctrl = self.has_ctrl and use_controlnet and ctrl_frames is not None
         cond = self._prepare(c, ctrl_frames if use_ctrl else None, B, T, h, w)
+        if self._graph_ok():
+            return self._forward_graphed(x, t, cond, B, T, h, w, use_ctrl)
+        x32 = x.to(dev, torch.float32).contiguous()
+        t32 = t.to(dev, torch.float32).contiguous()
+        return self._forward_body(x32, t32, cond, B, T, h, w, use_ctrl)
+
+    # ------------------------------------------------------------------------------------------------------------
+    # CUDA-graph replay of the step (all shapes are static over the 30 sampler steps of a chunk)
+    # ------------------------------------------------------------------------------------------------------------
+    def _graph_ok(self) -> bool:
+        return (self.use_cuda_graph and self.debug_taps is None and ops._PROFILE is None
+                and self.dev.type == "cuda")
+
+    def _forward_graphed(self, x, t, cond, B, T, h, w, use_ctrl):
+        """The ~1000 launches of one forward are recorded once per (shape, conditioning) into a CUDA graph on the
+        caller's stream and replayed: one cudaGraphLaunch per sampler step instead of ~1000 ctypes calls and 7
+        host-side tensor-map encodes per GEMM.  The first forward of a new shape runs eagerly (it fills the lazily
+        built caches: time-position embeddings, GroupNorm scratch, kernel attributes); the conditioning tensors
+        the graph points at are owned by the cache entry of `_prepare`, so a new conditioning (next chunk) is a
+        new capture (recording costs host time only, no kernel runs) into the same memory pool."""
+        key = (B, T, h, w, use_ctrl)
+        g = self._graphs.get(key)
+        N = B * T
+        if g is None:
+            # first visit of this shape: eager run (warms caches), static I/O buffers
+            g = dict(x=torch.empty((N, 4, h, w), dtype=torch.float32, device=self.dev),
+                     t=torch.empty((N,), dtype=torch.float32, device=self.dev), graph=None, epoch=-1, out=None,
+                     launches=0)
+            self._graphs[key] = g
+            g["x"].copy_(x, non_blocking=True)
+            g["t"].copy_(t, non_blocking=True)
+            return self._forward_body(g["x"], g["t"], cond, B, T, h, w, use_ctrl)
+        g["x"].copy_(x, non_blocking=True)
+        g["t"].copy_(t, non_blocking=True)
+        if g["graph"] is None or g["epoch"] != self._cond_epoch:
+            g["graph"] = None                      # release the previous recording before re-using its pool
+            g["out"] = None
+            graph = torch.cuda.CUDAGraph()
+            l0 = ops.launches()
+            torch.cuda.current_stream().synchronize()
+            with torch.cuda.graph(graph, pool=self._graph_pool, stream=self._capture_stream):
+                out = self._forward_body(g["x"], g["t"], cond, B, T, h, w, use_ctrl)
+            g.update(graph=graph, out=out, epoch=self._cond_epoch, launches=ops.launches() - l0)
+            ops._launch_count -= g["launches"]     # recording is not launching
+        g["graph"].replay()
+        ops._launch_count += g["launches"]
+        res = torch.empty_like(g["out"])
+        res.copy_(g["out"], non_blocking=True)     # D2D memcpy: the caller gets its own tensor, like the reference
+        return res
+
+    def _forward_body(self, x32, t32, cond, B, T, h, w, use_ctrl):
+        N = B * T
+        dev = self.dev
         Fc = self.cfg.num_frame_conditioning
         W = self.wu
         plan = self.plan_u

@@ -325,15 +325,20 @@ def small_attn(q, k, v, *, b, s, heads, lq, lk, kv_per_pixel=True, out=None):
 # norms
 # ----------------------------------------------------------------------------------------------------------------
 _GN_SCRATCH = {}
+_GN_RETIRED = []   # outgrown buffers stay allocated: a recorded CUDA graph may still point at them
 
 
 def _gn_scratch(device, doubles, n):
-    """Per-device scratch for the deterministic GroupNorm reduction (chunk partials + self-resetting tickets).
-    Kernels on one stream run in order, so one buffer per device is enough."""
-    key = str(device)
+    """Scratch of the deterministic GroupNorm reduction (chunk partials + self-resetting tickets), one per
+    (device, stream): kernels on one stream run in order, kernels on different streams (two wrappers, a wrapper and
+    the VAE decoder, a graph being recorded) must not share tickets.  Buffers are never freed or moved while the
+    process lives — CUDA graphs bake their addresses."""
+    key = (str(device), torch.cuda.current_stream().cuda_stream if device.type == "cuda" else 0)
     cur = _GN_SCRATCH.get(key)
     if cur is None or cur[0].numel() < doubles or cur[1].numel() < n:
-        cur = (torch.empty(max(doubles, 1 << 16), dtype=torch.float64, device=device),
+        if cur is not None:
+            _GN_RETIRED.append(cur)
+        cur = (torch.empty(max(doubles, 1 << 18), dtype=torch.float64, device=device),
                torch.zeros(max(n, 1024), dtype=torch.int32, device=device))
         _GN_SCRATCH[key] = cur
     return cur

@@ -106,6 +106,8 @@ class B200EulerEDMSampler:
         cond2 = self.prepare_cond(cond, cond if uc is None else uc)
         if self.cfg_parallel:
             cond2, kw = self._my_half(cond2, kw)
+            # both guidance halves must be evaluated on the same latent: rank 0's initial noise wins
+            x = dist_utils.broadcast_from_rank0(x.to(torch.float32).contiguous())
         # x *= sqrt(1 + sigma_0^2) (sampling.py:47): the first half of the doubling kernel's output
         x = ops.sampler_prepare(x.to(torch.float32).contiguous(), math.sqrt(1.0 + float(sigmas[0]) ** 2))[:x.shape[0]]
         for i in range(len(sigmas) - 1):

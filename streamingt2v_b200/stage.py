@@ -46,14 +46,14 @@ def _to_fchw(video: torch.Tensor) -> torch.Tensor:
 
 class B200StreamingSVDStage:
     def __init__(self, inference_model, sampler, vae_decoder, conditioner: Callable, *, num_conditional_frames: int = 7,
-                 anchor_frame: int = 0, scale_factor: float = SCALE_FACTOR, max_decode_chunk: int = MAX_DECODE_CHUNK,
+                 anchor_frame: int = 6, scale_factor: float = SCALE_FACTOR, max_decode_chunk: int = MAX_DECODE_CHUNK,
                  device="cuda:0", shard_decode: bool = False):
         self.inference_model = inference_model      # B200StreamingWrapper        (streaming_svd.py:50-56)
         self.sampler = sampler                      # B200EulerEDMSampler         (config.yaml:139-157)
         self.vae_decoder = vae_decoder              # B200VaeDecoder              (first_stage_model.decode)
         self.conditioner = conditioner
         self.num_conditional_frames = int(num_conditional_frames)
-        self.anchor_frame = int(anchor_frame)
+        self.anchor_frame = int(anchor_frame)           # inference_params.anchor_frames: '6' (config.yaml:316)
         self.scale_factor = float(scale_factor)
         self.max_decode_chunk = int(max_decode_chunk)
         self.device = torch.device(device)
@@ -113,6 +113,11 @@ class B200StreamingSVDStage:
             c[k] = c[k].repeat_interleave(T, dim=0)
         randn = torch.randn(shape, generator=generator, device=generator.device if generator is not None else "cpu")
         randn = randn.to(self.device)
+        if self.shard_decode or getattr(self.sampler, "cfg_parallel", False):
+            # every rank of a sharded step / decode must integrate the SAME latent: rank 0's noise wins (the ranks'
+            # generators are not assumed to be seeded alike).  The conditioner's cond_aug noise (streaming_svd.py:174)
+            # is drawn inside the injected callable and must be made rank-invariant there.
+            randn = dist_utils.broadcast_from_rank0(randn)
         extra = dict(image_only_indicator=torch.zeros(2 * batch_size, T, device=self.device), num_video_frames=T,
                      batch_size=2 * batch_size, num_conditional_frames=self.num_conditional_frames,
                      ctrl_frames=ctrl_frames)

@@ -45,7 +45,8 @@ def _worker(rank, world, port, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     x, cond, uc = _inputs()
     smp = sampler_mod.B200EulerEDMSampler(num_steps=4, num_frames=T, cfg_parallel=True)
-    out = smp(_fake_network, x.clone(), cond, uc, batch_size=2, num_video_frames=T,
+    # rank 1 deliberately starts from a DIFFERENT latent: the sampler must broadcast rank 0's (advisor finding r1)
+    out = smp(_fake_network, x.clone() + float(rank), cond, uc, batch_size=2, num_video_frames=T,
               image_only_indicator=torch.zeros(2, T))
     stage = B200StreamingSVDStage(None, smp, _StubDecoder(), None, device="cpu", shard_decode=True, max_decode_chunk=2)
     z = torch.randn(7, 4, 2, 3, generator=torch.Generator().manual_seed(4))       # 4 groups: 2, 2, 2, 1 frames

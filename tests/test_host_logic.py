@@ -44,6 +44,48 @@ def test_executor_wiring(patched_model, apm, T, h, w):
     assert eng._cond_key != key and not torch.equal(out, out3)
 
 
+def test_conditioning_cache_is_not_fooled_by_recycled_storage(patched_model):
+    """Regression (round-1 advisor finding): the conditioning cache used to be keyed on (data_ptr, _version, shape).
+    A caller that frees its conditioning tensors and builds new ones of equal shape usually gets the SAME address
+    back from the caching allocator with _version 0 -> stale ControlNet embedding / cross-attention vectors.  The
+    cache now keys on tensor identity and keeps the keyed tensors alive."""
+    from streamingt2v_b200 import arch, synth
+    cfg = arch.TINY
+    T, h, w = 8, 8, 8
+    sd_u = arch.synth_state_dict_fast(arch.unet_param_shapes(cfg), 41)
+    sd_c = arch.synth_state_dict_fast(arch.controlnet_param_shapes(cfg), 42)
+    eng = patched_model.B200Denoiser(cfg, sd_u, sd_c, "cpu")
+    x, t, c, kw = synth.make_inputs(cfg, T=T, h=h, w=w, seed=9)
+
+    def run(c_, ctrl_):
+        return eng.forward(x, t, c_, batch_size=2, num_video_frames=T, ctrl_frames=ctrl_)
+
+    ctrl = kw["ctrl_frames"]
+    out1 = run(c, ctrl)
+    epoch = eng._cond_epoch
+    ptrs = {k: v.data_ptr() for k, v in c.items()}
+    shapes = {k: v.shape for k, v in c.items()}
+    hits = 0
+    for trial in range(8):
+        # free the caller's tensors, then allocate same-shaped ones with different content (the per-call torch.cat
+        # of prepare_cond / a function-scoped ctrl_frames do exactly this)
+        del c
+        c = {k: torch.full(shapes[k], 0.1 * (trial + 1)) for k in shapes}
+        hits += sum(c[k].data_ptr() == ptrs[k] for k in c)
+        out2 = run(c, ctrl)
+        assert eng._cond_epoch == epoch + trial + 1, "stale conditioning reused for new tensors"
+        assert not torch.equal(out1, out2)
+        out1 = out2
+    # a new ctrl_frames tensor (same shape, new content) must also invalidate
+    ctrl2 = -ctrl.clone()
+    out3 = run(c, ctrl2)
+    assert not torch.equal(out3, out1)
+    # the entry holds references: the keyed tensors stay alive, so an equal address can only be the same object
+    assert all(a is b for a, b in zip(eng._cond_refs, (c["crossattn"], c["vector"], c["concat"], ctrl2)))
+    eng.reset_conditioning()
+    assert eng._cond_refs is None
+
+
 def test_no_controlnet_branch(patched_model):
     from oracle import streaming_svd_oracle as orc
     from streamingt2v_b200 import arch, synth
