@@ -2,9 +2,10 @@
 (code/diffusion_trainer/streaming_svd.py:124-151 decode_first_stage, :155-221 _generate_conditional_output,
 :263-290 extract_ctrl_frames, :293-356 _autoregressive_generation; utils/result_processor.py:4-14 convert_range)
 with the heavy components passed in as callables, written independently of streamingt2v_b200/stage.py (explicit
-python loops over frames and chunks).  The reference methods themselves cannot run here (hard-coded "cuda",
-Lightning / OpenCLIP / IImage dependencies), so this row is checked as host logic: same calls, same order, same
-frames."""
+python loops over frames and chunks).  Pinned against the reference: oracle/make_golden_stage.py executes the UNMODIFIED reference methods (unbound, on a
+mock `self`, CPU) with the stand-in components of oracle/stage_stubs.py and stores what they produce in
+tests/golden/stage_reference.npz; tests/test_stage.py replays that scenario through this file and through
+streamingt2v_b200/stage.py."""
 from __future__ import annotations
 
 import math

@@ -76,12 +76,64 @@ def test_stage_driver_matches_oracle_cpu():
     assert dec.sizes == [(4, 4), (2, 2)] * 3                      # ceil(6/4) rounds of <= 4 frames
     # with the reference's group size the whole video is identical to the oracle's
     smp8, dec8 = _StubSampler(), _StubDecoder()
-    stage8 = B200StreamingSVDStage(None, smp8, dec8, _conditioner, num_conditional_frames=NCOND, device="cpu")
+    stage8 = B200StreamingSVDStage(None, smp8, dec8, _conditioner, num_conditional_frames=NCOND, anchor_frame=0,
+                                   device="cpu")
     video8 = stage8.autoregressive_generation(first, 3, generator=torch.Generator().manual_seed(11))
     assert dec8.sizes == [(T, T)] * 3
     assert torch.allclose(video8, ref, rtol=0, atol=1e-4)
     for call, ctrl in zip(smp8.calls, ctrl_seen):
         assert torch.allclose(call["ctrl"], ctrl, rtol=0, atol=1e-5)
+
+
+def test_stage_driver_matches_unmodified_reference_methods():
+    """Row a22 pinned against the reference itself: tests/golden/stage_reference.npz was produced by the UNMODIFIED
+    `StreamingSVD._autoregressive_generation` (+ _generate_conditional_output, extract_ctrl_frames,
+    decode_first_stage, get_batch_sgm) running on a mock `self` with the stand-in components of
+    oracle/stage_stubs.py (oracle/make_golden_stage.py).  The same scenario through B200StreamingSVDStage must give
+    the same video, the same keyword arguments at the network and the same decode grouping."""
+    import os
+
+    from oracle import stage_oracle
+    from oracle import stage_stubs as st
+    from streamingt2v_b200.stage import B200StreamingSVDStage
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "stage_reference.npz"))
+    T_, ncond, anchor, n_gen, seed = (int(v) for v in g["meta"])
+    network, decoder = st.StubNetwork(), st.StubDecoder()
+    stage = B200StreamingSVDStage(network, st.B200StyleSampler(T_), decoder, st.b200_style_conditioner,
+                                  num_conditional_frames=ncond, device="cpu")
+    assert stage.anchor_frame == anchor == 6          # default = inference_params.anchor_frames '6' (config.yaml:316)
+    torch.manual_seed(seed)                            # conditioner noise + initial noise from the global RNG, like
+    video = stage.autoregressive_generation(st.first_chunk(), n_gen)     # the reference (streaming_svd.py:174,196)
+    # the reference hands the [0,255] float video to its IImage container, which stores uint8 [F,H,W,C]
+    # (lib/farancia/libimage/iimage.py torch2np: 255 * (x.clip(vmin, vmax) - vmin) / (vmax - vmin) -> uint8)
+    u8 = (255 * (video.clip(0, 255) - 0) / (255 - 0)).permute(0, 2, 3, 1).to(torch.uint8).numpy()
+    assert u8.shape == g["video_u8"].shape
+    assert np.array_equal(u8, g["video_u8"]), int(np.abs(u8.astype(int) - g["video_u8"].astype(int)).max())
+    assert decoder.sizes == [tuple(r) for r in g["decode_sizes"].tolist()]
+    calls = network.calls
+    got = np.array([[c["n"], c["bs"], c["nvf"], c["ncf"], c["ioi"][0], c["ioi"][1]] for c in calls], np.int64)
+    assert np.array_equal(got, g["net_calls"])
+    assert tuple(calls[0]["ctrl_shape"]) == tuple(g["ctrl_shape"].tolist())
+    assert np.allclose([c["ctrl_sum"] for c in calls], g["ctrl_sums"], rtol=1e-6, atol=1e-6)
+    assert np.allclose([c["vec_sum"] for c in calls], g["vec_sums"], rtol=1e-6, atol=1e-6)
+    # and the independent restatement (oracle/stage_oracle.py) agrees with the reference as well
+    torch.manual_seed(seed)
+    net2 = st.StubNetwork()
+    smp = st.B200StyleSampler(T_)
+
+    def conditioner(frame, n):
+        return st.b200_style_conditioner(frame, n)
+
+    def sample(noise, c, uc, ctrl):
+        return smp(net2, noise, c, uc, image_only_indicator=torch.zeros(2, T_), num_video_frames=T_, batch_size=2,
+                   num_conditional_frames=ncond, ctrl_frames=ctrl)
+
+    H, W = st.first_chunk().shape[-2:]
+    ref_video, _ = stage_oracle.autoregressive_generation(
+        st.first_chunk(), n_gen, conditioner=conditioner, sample=sample, decode=lambda z, n: st.decode_math(z, n),
+        num_frames=T_, n_cond=ncond, anchor=anchor, noise=lambda i: torch.randn((T_, 4, H // 8, W // 8)))
+    u8o = (255 * (ref_video.clip(0, 255) - 0) / 255).permute(0, 2, 3, 1).to(torch.uint8).numpy()
+    assert np.array_equal(u8o, g["video_u8"])
 
 
 def test_decode_first_stage_chunking():
