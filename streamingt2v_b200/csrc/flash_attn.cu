@@ -12,8 +12,8 @@
 // before its current softmax finishes (with one buffer per tile the softmax warps idled through their own
 // PV -> QK round trip and the MUFU pipe sat at 56%, profiles/r01_ncu_fa_v2_details.txt).
 //   warp 0      TMA producer (Q_A, Q_B once; K/V ring of 4 stages)
-//   warp 1      MMA issuer + TMEM owner
-//   warps 2..9  softmax: 4 warps per query tile, one query row per thread
+//   warp 1      MMA issuer + TMEM owner          (warps 2, 3 idle: warpgroup 0 gives its registers away, setmaxnreg)
+//   warps 4..11 softmax: one warpgroup per query tile, one query row per thread, 224 registers per thread
 // Per 128-key block and tile:
 //   MMA : S[128x128] = Q K_j^T                       (4 x tcgen05.mma M128 N128 K16, fp32 in TMEM)
 //   SM  : one pass over the row in registers: block max, lazy running-max update, P = exp2(S*c - m*c),
@@ -41,7 +41,7 @@ constexpr int FA_Q_BYTES = FA_BQ * FA_D * 2;        // 16 KB per query tile
 constexpr int FA_KV_TILE_BYTES = FA_BK * FA_D * 2;  // 16 KB each for K and V
 constexpr int FA_SMEM_BYTES = 2 * FA_Q_BYTES + FA_KV_STAGES * 2 * FA_KV_TILE_BYTES + 256;
 constexpr int FA_TMEM_COLS = 512;  // score buffers [0,128) [128,256) [256,384) (P aliases the first 64 columns), O_A [384,448) O_B [448,512)
-constexpr int FA_THREADS = 10 * 32;
+constexpr int FA_THREADS = 12 * 32;  // warpgroup 0: TMA, MMA (+2 idle warps); warpgroups 1, 2: softmax of tile A, B
 constexpr float FA_RESCALE_THRESHOLD = 8.0f;  // log2 units
 constexpr int FA_POLY_DEFAULT = 0;  // measured (tools/bench_fa.py): every 1/8 moved to the FMA pipe costs ~5%: the softmax
                                     // warps are bound by their own dependent-latency chain, not by MUFU throughput
@@ -55,7 +55,13 @@ struct FaParams {
 
 // POLY: how many of every 8 score pairs take their exp2 on the FMA pipe (ex2_poly) instead of MUFU.  The softmax
 // of a 128 x 128 tile needs 2x the MUFU time of the tile's MMAs (16 ex2/clk/SM), so the kernel is MUFU-bound.
-template <int POLY>
+// FAST (v4 softmax): every key block after the first is handled in ONE pass over the scores.  The probabilities are
+// computed optimistically against the running max the row already uses while the block max is tracked on the side;
+// only if some row's block max exceeds its running max by more than 2^8 (rare after the first blocks) the block
+// falls back to the two-pass path below (rescale O and l, recompute P against the raised max).  TMEM loads are
+// software pipelined (next 32 columns in flight while the current 32 are processed), the scale/subtract and the
+// row-sum use packed FFMA2/FADD2, the max uses FMNMX3: ~3 issue slots per score instead of ~4.6, no MUFU-idle max pass.
+template <int POLY, bool FAST>
 __global__ void __launch_bounds__(FA_THREADS, 1)
 flash_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const FaParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];  // SWIZZLE_128B tiles need 1024-byte alignment
@@ -99,7 +105,11 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const FaParams p) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
+  // register re-allocation between the warpgroups: the softmax rows keep 64 packed probabilities, two 32-score
+  // buffers in flight and the running statistics live (the 168-register compile-time cap spilled them)
+  if (warp < 4) {
+   asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+   if (warp == 0) {
     if (lane == 0) {
       // ===================== TMA producer =====================
       mbar_expect_tx(q_full, 2 * FA_Q_BYTES);
@@ -158,9 +168,11 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const FaParams p) {
       }
     }
     __syncwarp();
+   }
   } else {
-    // ===================== softmax warps: tile x = (warp-2)/4, TMEM lane quadrant = warp % 4 =====================
-    const int x = (warp - 2) >> 2;
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    // ===================== softmax warps: tile x = (warp-4)/4, TMEM lane quadrant = warp % 4 =====================
+    const int x = (warp - 4) >> 2;
     const int qd = warp & 3;
     const int r = qd * 32 + lane;  // query row in tile == TMEM lane
     const uint32_t tl = ((uint32_t)(qd * 32)) << 16;
@@ -173,10 +185,75 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const FaParams p) {
       const uint32_t tS = tmem_base + bf * 128 + tl;
       mbar_wait(&s_full[bf], (k / 3) & 1);
       tc_fence_after();
-      // pass 1 over the row (TMEM reads are cheap; keeping all 128 scores live would exceed the 168-register
-      // budget that 10 warps per CTA leave per thread): block max
       const int kbase = j * FA_BK;
       const bool tail = kbase + FA_BK > p.S;
+      if (FAST && j > 0 && !tail) {
+        const float mbf = m_used * c;
+        const f32x2 c2 = pack2(c, c), nmb2 = pack2(-mbf, -mbf);
+        f32x2 la = pack2(0.f, 0.f), lb = pack2(0.f, 0.f);
+        float mxa = -INFINITY, mxb = -INFINITY;
+        uint32_t pkf[64];
+        uint32_t sva[32], svb[32];
+        auto process = [&](const uint32_t (&sv)[32], const int pbase) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float s0 = __uint_as_float(sv[2 * i]), s1 = __uint_as_float(sv[2 * i + 1]);
+            if (i & 1) mxb = max3f(mxb, s0, s1);
+            else mxa = max3f(mxa, s0, s1);
+            const f32x2 x2 = fma2(pack2(s0, s1), c2, nmb2);
+            float a, b;
+            if ((i & 7) < POLY) {
+              ex2_poly2(x2, a, b);
+            } else {
+              float xa, xb;
+              unpack2(x2, xa, xb);
+              a = ex2_approx(xa);
+              b = ex2_approx(xb);
+            }
+            if (i & 1) lb = add2(lb, pack2(a, b));
+            else la = add2(la, pack2(a, b));
+            pkf[pbase + i] = pack_bf16x2(a, b);
+          }
+        };
+        tmem_ld32(tS, sva);
+        tmem_ld_wait32(sva);
+        tmem_ld32(tS + 32, svb);
+        process(sva, 0);
+        tmem_ld_wait32(svb);
+        tmem_ld32(tS + 64, sva);
+        process(svb, 16);
+        tmem_ld_wait32(sva);
+        tmem_ld32(tS + 96, svb);
+        process(sva, 32);
+        tmem_ld_wait32(svb);
+        process(svb, 48);
+        const float mxf = fmaxf(mxa, mxb);
+        const bool needf = (mxf - m_used) * c > FA_RESCALE_THRESHOLD;
+        if (!__any_sync(0xffffffffu, needf)) {
+          {
+            uint32_t t0[32], t1[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              t0[i] = pkf[i];
+              t1[i] = pkf[32 + i];
+            }
+            tmem_st32(tS + 0, t0);
+            tmem_st32(tS + 32, t1);
+          }
+          float l0, l1, l2, l3;
+          unpack2(la, l0, l1);
+          unpack2(lb, l2, l3);
+          l_run += (l0 + l1) + (l2 + l3);
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&p_full[bf]);
+          continue;
+        }
+        // rare: some row's max rose by more than the threshold -> redo this block on the two-pass path (S is intact)
+      }
+      // pass 1 over the row (TMEM reads are cheap; keeping all 128 scores live would exceed the 168-register
+      // budget that 10 warps per CTA leave per thread): block max
       float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
       for (int c0 = 0; c0 < FA_BK; c0 += 32) {
@@ -319,21 +396,27 @@ extern "C" int b200svd_flash_attn(const void* qkv, int64_t ldqkv, void* out, int
   uint64_t strides[2] = {(uint64_t)ldqkv * 2, (uint64_t)ldqkv * 2 * (uint64_t)s};
   uint32_t box[3] = {64, 128, 1};
   if (encode_tmap_bf16(&tm, qkv, 3, dims, strides, box)) return 1;
-  // exp2 split between MUFU and the FMA pipe: B200SVD_FA_POLY = 0..4 of every 8 score pairs (tuning knob)
-  static int poly = -1;
+  // exp2 split between MUFU and the FMA pipe: B200SVD_FA_POLY = 0..4 of every 8 score pairs; B200SVD_FA_V = 3 selects
+  // the round-1 two-pass softmax, 4 (default) the single-pass one (tuning knobs)
+  static int poly = -1, fast = 1;
   if (poly < 0) {
     const char* ev = getenv("B200SVD_FA_POLY");
     poly = ev ? atoi(ev) : FA_POLY_DEFAULT;
     if (poly < 0 || poly > 4) poly = FA_POLY_DEFAULT;
+    const char* fv = getenv("B200SVD_FA_V");
+    fast = (fv && atoi(fv) == 3) ? 0 : 1;
     cudaError_t e = cudaSuccess;
     auto set = [&](auto kern) {
       if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_BYTES);
     };
-    set(flash_attn_kernel<0>);
-    set(flash_attn_kernel<1>);
-    set(flash_attn_kernel<2>);
-    set(flash_attn_kernel<3>);
-    set(flash_attn_kernel<4>);
+    set(flash_attn_kernel<0, false>);
+    set(flash_attn_kernel<1, false>);
+    set(flash_attn_kernel<2, false>);
+    set(flash_attn_kernel<0, true>);
+    set(flash_attn_kernel<1, true>);
+    set(flash_attn_kernel<2, true>);
+    set(flash_attn_kernel<3, true>);
+    set(flash_attn_kernel<4, true>);
     if (e != cudaSuccess) {
       poly = -1;
       return cuda_fail(e, "cudaFuncSetAttribute(flash_attn)");
@@ -348,12 +431,20 @@ extern "C" int b200svd_flash_attn(const void* qkv, int64_t ldqkv, void* out, int
   p.scale_log2 = scale * 1.4426950408889634f;
   dim3 grid((s + 2 * FA_BQ - 1) / (2 * FA_BQ), heads, n);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  switch (poly) {
-    case 0: flash_attn_kernel<0><<<grid, FA_THREADS, FA_SMEM_BYTES, st>>>(tm, p); break;
-    case 1: flash_attn_kernel<1><<<grid, FA_THREADS, FA_SMEM_BYTES, st>>>(tm, p); break;
-    case 2: flash_attn_kernel<2><<<grid, FA_THREADS, FA_SMEM_BYTES, st>>>(tm, p); break;
-    case 3: flash_attn_kernel<3><<<grid, FA_THREADS, FA_SMEM_BYTES, st>>>(tm, p); break;
-    default: flash_attn_kernel<4><<<grid, FA_THREADS, FA_SMEM_BYTES, st>>>(tm, p); break;
+  if (fast) {
+    switch (poly) {
+      case 0: flash_attn_kernel<0, true><<<grid, FA_THREADS, FA_SMEM_BYTES, st>>>(tm, p); break;
+      case 1: flash_attn_kernel<1, true><<<grid, FA_THREADS, FA_SMEM_BYTES, st>>>(tm, p); break;
+      case 2: flash_attn_kernel<2, true><<<grid, FA_THREADS, FA_SMEM_BYTES, st>>>(tm, p); break;
+      case 3: flash_attn_kernel<3, true><<<grid, FA_THREADS, FA_SMEM_BYTES, st>>>(tm, p); break;
+      default: flash_attn_kernel<4, true><<<grid, FA_THREADS, FA_SMEM_BYTES, st>>>(tm, p); break;
+    }
+  } else {
+    switch (poly) {
+      case 0: flash_attn_kernel<0, false><<<grid, FA_THREADS, FA_SMEM_BYTES, st>>>(tm, p); break;
+      case 1: flash_attn_kernel<1, false><<<grid, FA_THREADS, FA_SMEM_BYTES, st>>>(tm, p); break;
+      default: flash_attn_kernel<2, false><<<grid, FA_THREADS, FA_SMEM_BYTES, st>>>(tm, p); break;
+    }
   }
   B200_CHECK_LAUNCH("flash_attn");
   return 0;

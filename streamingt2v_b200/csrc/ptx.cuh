@@ -184,6 +184,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "r"(taddr)
       : "memory");
 }
+// wait::ld that also names the destination registers: the loads complete asynchronously, so every use of the values
+// must be ordered after the wait — as operands they are, for the compiler too (software-pipelined loads).
+__device__ __forceinline__ void tmem_ld_wait32(uint32_t (&v)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                 "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]),
+                 "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]),
+                 "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+               :
+               : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // registers -> TMEM (this warp's 32 lanes x 16 columns)
@@ -335,6 +346,56 @@ __device__ __forceinline__ float ex2_poly(float x) {
   pl = fmaf(pl, f, 0.6931472f);
   pl = fmaf(pl, f, 1.0f);
   return __uint_as_float(__float_as_uint(pl) + (__float_as_uint(t) << 23));
+}
+// ---- packed fp32 pairs (FFMA2 / FADD2: two fp32 lanes per instruction on sm_100) and 3-input max (FMNMX3) ----
+struct f32x2 {
+  uint64_t v;
+};
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ f32x2 pack2u(uint32_t lo, uint32_t hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 a, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v));
+  return r;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+  return r;
+}
+__device__ __forceinline__ float max3f(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+// exp2 of a PAIR on the FMA pipe (same polynomial as ex2_poly): 5 packed FMA-pipe instructions + 2 clamps + 2 integer
+// exponent patches for two results, against 2 MUFU instructions.
+__device__ __forceinline__ void ex2_poly2(f32x2 x, float& ra, float& rb) {
+  float xa, xb;
+  unpack2(x, xa, xb);
+  x = pack2(fmaxf(xa, -126.0f), fmaxf(xb, -126.0f));
+  const f32x2 magic = pack2(12582912.0f, 12582912.0f), nmagic = pack2(-12582912.0f, -12582912.0f);
+  const f32x2 t = add2(x, magic);                       // low mantissa bits hold round(x)
+  const f32x2 f = fma2(add2(t, nmagic), pack2(-1.0f, -1.0f), x);   // x - round(x) in [-0.5, 0.5]
+  f32x2 pl = fma2(pack2(0.0555041f, 0.0555041f), f, pack2(0.2402265f, 0.2402265f));
+  pl = fma2(pl, f, pack2(0.6931472f, 0.6931472f));
+  pl = fma2(pl, f, pack2(1.0f, 1.0f));
+  float pa, pb, ta, tb;
+  unpack2(pl, pa, pb);
+  unpack2(t, ta, tb);
+  ra = __uint_as_float(__float_as_uint(pa) + (__float_as_uint(ta) << 23));
+  rb = __uint_as_float(__float_as_uint(pb) + (__float_as_uint(tb) << 23));
 }
 __device__ __forceinline__ float rcp_approx(float x) {
   float y;

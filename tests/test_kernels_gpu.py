@@ -38,6 +38,26 @@ def test_flash_attn(cuda_dev, n, s, heads):
     _check(out, ref, f"flash_attn n{n} s{s} h{heads}", rtol=2 ** -6, atol=2e-2)
 
 
+@pytest.mark.parametrize("s,ramp", [(1024, 6.0), (2304, 3.0), (640, 12.0)])
+def test_flash_attn_rising_max(cuda_dev, s, ramp):
+    """Key magnitudes grow along the sequence, so the row maxima keep rising by more than 2^8 between key blocks: the
+    single-pass softmax must take its redo path (rescale O and l, recompute P) and still match SDPA."""
+    from streamingt2v_b200 import ops
+    n, heads = 2, 3
+    Cc = heads * 64
+    g = torch.Generator(device="cpu").manual_seed(s)
+    q = torch.randn(n * s, Cc, generator=g) * 2.0
+    k = torch.randn(n * s, Cc, generator=g) * (0.1 + ramp * (torch.arange(n * s) % s)[:, None] / s)
+    k = k + 0.5 * torch.sign(q)                       # correlate: the large late keys really win the softmax
+    v = torch.randn(n * s, Cc, generator=g)
+    qkv = torch.cat([q, k, v], 1).to(cuda_dev).to(torch.bfloat16)
+    out = ops.flash_attn(qkv, n, s, heads)
+    torch.cuda.synchronize()
+    qf, kf, vf = (t.float().reshape(n, s, heads, 64).permute(0, 2, 1, 3) for t in qkv.chunk(3, dim=1))
+    ref = F.scaled_dot_product_attention(qf, kf, vf).permute(0, 2, 1, 3).reshape(n * s, Cc)
+    _check(out, ref, f"flash_attn rising max s{s} ramp{ramp}", rtol=2 ** -6, atol=2e-2)
+
+
 @pytest.mark.parametrize("b,s,heads,lq,lk,pp", [(2, 64, 5, 8, 8, True), (2, 144, 10, 25, 25, True),
                                                 (2, 100, 5, 25, 7, True), (1, 333, 20, 25, 17, False),
                                                 (2, 4, 5, 8, 7, True)])

@@ -20,4 +20,4 @@ for n, s, h in [(50, 9216, 5), (50, 2304, 10), (50, 576, 20)]:
     ref = torch.softmax(q @ kf.transpose(-1, -2) * 0.125, -1) @ vf
     got = out.float().reshape(n, s, h, 64).permute(0, 2, 1, 3)[:1, :2, :256]
     err = (got - ref).abs().max().item()
-    print(f"POLY={os.environ.get('B200SVD_FA_POLY', 'default')} n{n} s{s} h{h}: {ms:.3f} ms {fl / ms / 1e9:.0f} TF/s  max_abs_err {err:.2e}", flush=True)
+    print(f"V={os.environ.get('B200SVD_FA_V', '4')} POLY={os.environ.get('B200SVD_FA_POLY', 'default')} n{n} s{s} h{h}: {ms:.3f} ms {fl / ms / 1e9:.0f} TF/s  max_abs_err {err:.2e}", flush=True)
