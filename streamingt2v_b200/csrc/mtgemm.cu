@@ -110,7 +110,11 @@ __device__ __forceinline__ void decode_tile(const GemmDev& p, uint32_t tile, uin
   mb3 = t3 << p.m_lb[2];
 }
 
-template <int BN, int CL>
+// EPI: 0 = generic epilogue (bias / per-frame vector / activation / two residuals, all run-time switches);
+//      1 = GEGLU with bias and nothing else (the FF1 projections, 17 % of the step): compile-time specialised, packed
+//          FFMA2 math (ptx.cuh geglu2) — the generic loop spent ~30 issue slots per output there and bound the K = 320
+//          layer at 0.45 of the tensor rate (profiles/r01_ncu_v4_geglu_details.txt).
+template <int BN, int CL, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 mtgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAh,
               const __grid_constant__ CUtensorMap tmB,
@@ -396,7 +400,131 @@ mtgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         }
       };
 
-      if (!skip && p.tma_epi) {
+      if (EPI == 1) {
+        if (!skip) {
+          // host guarantees: act == GEGLU, 16-byte aligned bias, no fvec / residuals, s_acc == 1, TMA-store epilogue,
+          // n % BN == 0 (every 64-column block is full)
+          if (lane == 0) tma_store_wait_read<0>();  // the previous TMA store has finished reading the staging block
+          __syncwarp();
+          uint8_t* orow = ob + lane * 128;
+          const uint32_t x = (uint32_t)(lane & 7);
+          const float4* bvp = reinterpret_cast<const float4*>(p.bias + n0 + 64 * s);
+          const float4* bgp = reinterpret_cast<const float4*>(p.bias + n0 + (uint32_t)(BN / 2) + 64 * s);
+#pragma unroll
+          for (uint32_t c = 0; c < 4; ++c) {
+            uint32_t va[16], vg[16];
+            tmem_ld16(tlane + 64 * s + 16 * c, va);
+            tmem_ld16(tlane + (uint32_t)(BN / 2) + 64 * s + 16 * c, vg);
+            tmem_ld_wait();
+            uint32_t o[8];
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const float4 bv = __ldg(bvp + 4 * c + j4);
+              const float4 bg = __ldg(bgp + 4 * c + j4);
+              const f32x2 v01 = add2(pack2u(va[4 * j4], va[4 * j4 + 1]), pack2(bv.x, bv.y));
+              const f32x2 v23 = add2(pack2u(va[4 * j4 + 2], va[4 * j4 + 3]), pack2(bv.z, bv.w));
+              const f32x2 g01 = add2(pack2u(vg[4 * j4], vg[4 * j4 + 1]), pack2(bg.x, bg.y));
+              const f32x2 g23 = add2(pack2u(vg[4 * j4 + 2], vg[4 * j4 + 3]), pack2(bg.z, bg.w));
+              float r0, r1, r2, r3;
+              unpack2(geglu2(v01, g01), r0, r1);
+              unpack2(geglu2(v23, g23), r2, r3);
+              o[2 * j4] = pack_bf16x2(r0, r1);
+              o[2 * j4 + 1] = pack_bf16x2(r2, r3);
+            }
+            *reinterpret_cast<uint4*>(orow + (((2 * c) ^ x) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<uint4*>(orow + (((2 * c + 1) ^ x) << 4)) = make_uint4(o[4], o[5], o[6], o[7]);
+          }
+          fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA store
+        }
+      } else if (EPI == 2) {
+        if (!skip) {
+          // linear family without activation: acc (+ bias) (+ per-frame vector) (* s_acc) (+ s1 res1) (+ s2 res2), all
+          // optional parts behind warp-uniform branches, arithmetic on packed pairs.  Host guarantees: TMA-store
+          // epilogue, n_out % 16 == 0 (a 16-column chunk is either complete or entirely past the edge), 16-byte
+          // aligned bias / fvec (ldf % 4 == 0).  ~4 issue slots per output instead of ~20.
+          if (use_res_ring) {
+            mbar_wait(my_res, rcount & 1);  // residual block has landed in the staging block
+            ++rcount;
+          } else {
+            if (lane == 0) tma_store_wait_read<0>();
+            __syncwarp();
+          }
+          uint8_t* orow;
+          uint32_t x;
+          if (subw == 64) {
+            orow = ob + lane * 128;
+            x = (uint32_t)(lane & 7);
+          } else {
+            orow = ob + lane * 64;
+            x = (uint32_t)((lane >> 1) & 3);
+          }
+          const uint32_t nchunks = subw >> 4;
+          const f32x2 s1v = splat2(p.s1), s2v = splat2(p.s2), sav = splat2(p.s_acc);
+          const bool has_res2 = p.res2 != nullptr && valid;
+#pragma unroll
+          for (uint32_t c = 0; c < 4; ++c) {
+            if (c < nchunks) {
+              const uint32_t acol = 64 * s + 16 * c;
+              const uint32_t ocol = ocol0 + 16 * c;
+              uint32_t va[16];
+              tmem_ld16(tlane + acol, va);
+              tmem_ld_wait();
+              f32x2 v[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = pack2u(va[2 * j], va[2 * j + 1]);
+              const bool inb = (ocol + 16) <= n_out;  // else: the whole chunk is past the N edge (TMA clips it)
+              if (p.bias != nullptr && inb) {
+                const float4* bp = reinterpret_cast<const float4*>(p.bias + n0 + acol);
+#pragma unroll
+                for (int j4 = 0; j4 < 4; ++j4) {
+                  const float4 bb = __ldg(bp + j4);
+                  v[2 * j4] = add2(v[2 * j4], pack2(bb.x, bb.y));
+                  v[2 * j4 + 1] = add2(v[2 * j4 + 1], pack2(bb.z, bb.w));
+                }
+              }
+              if (fv != nullptr && inb) {
+                const float4* fp = reinterpret_cast<const float4*>(fv + ocol);
+#pragma unroll
+                for (int j4 = 0; j4 < 4; ++j4) {
+                  const float4 bb = __ldg(fp + j4);
+                  v[2 * j4] = add2(v[2 * j4], pack2(bb.x, bb.y));
+                  v[2 * j4 + 1] = add2(v[2 * j4 + 1], pack2(bb.z, bb.w));
+                }
+              }
+              if (p.s_acc != 1.0f) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = mul2(v[j], sav);
+              }
+              const uint32_t c_lo = 2 * c, c_hi = 2 * c + 1;
+              if (use_res_ring) {
+                const uint4 a = *reinterpret_cast<const uint4*>(orow + ((c_lo ^ x) << 4));
+                const uint4 bq = *reinterpret_cast<const uint4*>(orow + ((c_hi ^ x) << 4));
+                const uint32_t w[8] = {a.x, a.y, a.z, a.w, bq.x, bq.y, bq.z, bq.w};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = fma2(pack2(bf16_lo(w[j]), bf16_hi(w[j])), s1v, v[j]);
+              }
+              if (has_res2 && inb) {
+                const uint4* rp = reinterpret_cast<const uint4*>(p.res2 + row * p.ld2 + ocol);
+                const uint4 a = __ldg(rp);
+                const uint4 bq = __ldg(rp + 1);
+                const uint32_t w[8] = {a.x, a.y, a.z, a.w, bq.x, bq.y, bq.z, bq.w};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = fma2(pack2(bf16_lo(w[j]), bf16_hi(w[j])), s2v, v[j]);
+              }
+              uint32_t o[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                float lo, hi;
+                unpack2(v[j], lo, hi);
+                o[j] = pack_bf16x2(lo, hi);
+              }
+              *reinterpret_cast<uint4*>(orow + ((c_lo ^ x) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+              *reinterpret_cast<uint4*>(orow + ((c_hi ^ x) << 4)) = make_uint4(o[4], o[5], o[6], o[7]);
+            }
+          }
+          fence_proxy_async_smem();
+        }
+      } else if (!skip && p.tma_epi) {
         if (use_res_ring) {
           mbar_wait(my_res, rcount & 1);  // residual block has landed in the staging block
           ++rcount;
@@ -571,7 +699,7 @@ static int encode_rows_view(CUtensorMap* tm, const void* base, int64_t ld, uint3
   return box_cols == 64 ? encode_tmap_bf16(tm, base, 5, dims, str, box) : encode_tmap_bf16_sw64(tm, base, 5, dims, str, box);
 }
 
-template <int BN, int CL>
+template <int BN, int CL, int EPI = 0>
 static int launch(const b200svd_gemm_params* p, const CUtensorMap& tmA, const GemmDev& d, cudaStream_t st) {
   using Cfg = TileCfg<BN, CL>;
   constexpr bool PAIR = CL >= 2;
@@ -626,7 +754,7 @@ static int launch(const b200svd_gemm_params* p, const CUtensorMap& tmA, const Ge
   }
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(mtgemm_kernel<BN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(mtgemm_kernel<BN, CL, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(mtgemm)");
     attr_set = true;
   }
@@ -653,7 +781,7 @@ static int launch(const b200svd_gemm_params* p, const CUtensorMap& tmA, const Ge
       qc.attrs = qa;
       qc.numAttrs = 1;
       int nc = 0;
-      if (cudaOccupancyMaxActiveClusters(&nc, mtgemm_kernel<BN, CL>, &qc) == cudaSuccess && nc > 0 && nc < max_clusters)
+      if (cudaOccupancyMaxActiveClusters(&nc, mtgemm_kernel<BN, CL, EPI>, &qc) == cudaSuccess && nc > 0 && nc < max_clusters)
         max_clusters = nc;
       else
         (void)cudaGetLastError();
@@ -676,7 +804,7 @@ static int launch(const b200svd_gemm_params* p, const CUtensorMap& tmA, const Ge
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, mtgemm_kernel<BN, CL>, tmA, tmAh, tmB, tmO64, tmO32, tmR64, tmR32, dd);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, mtgemm_kernel<BN, CL, EPI>, tmA, tmAh, tmB, tmO64, tmO32, tmR64, tmR32, dd);
   if (e != cudaSuccess) return cuda_fail(e, "mtgemm launch");
   return 0;
 }
@@ -814,14 +942,42 @@ extern "C" int b200svd_gemm(const b200svd_gemm_params* p, void* stream) {
   // mode 3: two pairs on adjacent N tiles share (multicast) their A tile when the N tile count is even
   const uint32_t n_tiles_all = (p->n + (uint32_t)bn - 1) / (uint32_t)bn;
   const bool quad = pair && pm == 3 && (n_tiles_all % 2) == 0;
+  // lean epilogue for everything without an activation (B200SVD_LEAN_EPI=0 keeps the generic loop: A/B knob)
+  static int lean_epi = -1;
+  if (lean_epi < 0) {
+    const char* e = getenv("B200SVD_LEAN_EPI");
+    lean_epi = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  const uint32_t n_out_h = p->act == B200SVD_ACT_GEGLU ? p->n / 2 : p->n;
+  const bool lean = lean_epi && p->act == B200SVD_ACT_NONE && d.tma_epi && (n_out_h % 16) == 0 &&
+                    (p->bias == nullptr || al16(p->bias)) &&
+                    (p->fvec == nullptr || (al16(p->fvec) && (p->ldf % 4) == 0)) && !quad;
+  if (lean) {
+    switch (bn) {
+      case 128: return pair ? launch<128, 2, 2>(p, tmA, d, st) : launch<128, 1, 2>(p, tmA, d, st);
+      case 160: return pair ? launch<160, 2, 2>(p, tmA, d, st) : launch<160, 1, 2>(p, tmA, d, st);
+      case 256: return pair ? launch<256, 2, 2>(p, tmA, d, st) : launch<256, 1, 2>(p, tmA, d, st);
+      default: break;
+    }
+  }
   switch (bn) {
     case 32: return launch<32, 1>(p, tmA, d, st);
     case 64: return launch<64, 1>(p, tmA, d, st);
     case 128: return pair ? launch<128, 2>(p, tmA, d, st) : launch<128, 1>(p, tmA, d, st);
     case 160:
       return quad ? launch<160, 4>(p, tmA, d, st) : pair ? launch<160, 2>(p, tmA, d, st) : launch<160, 1>(p, tmA, d, st);
-    case 256:
+    case 256: {
+      // specialised GEGLU epilogue (bias only); B200SVD_GEGLU_EPI=0 keeps the generic loop (A/B knob)
+      static int geglu_fast = -1;
+      if (geglu_fast < 0) {
+        const char* e = getenv("B200SVD_GEGLU_EPI");
+        geglu_fast = (e && atoi(e) == 0) ? 0 : 1;
+      }
+      const bool g1 = geglu_fast && p->act == B200SVD_ACT_GEGLU && d.tma_epi && p->bias != nullptr && al16(p->bias) &&
+                      p->fvec == nullptr && p->res1 == nullptr && p->res2 == nullptr && p->s_acc == 1.0f && !quad;
+      if (g1) return pair ? launch<256, 2, 1>(p, tmA, d, st) : launch<256, 1, 1>(p, tmA, d, st);
       return quad ? launch<256, 4>(p, tmA, d, st) : pair ? launch<256, 2>(p, tmA, d, st) : launch<256, 1>(p, tmA, d, st);
+    }
     default: set_error("b200svd_gemm: unsupported N tile %d", bn); return 1;
   }
 }
