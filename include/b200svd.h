@@ -167,6 +167,18 @@ int b200svd_sampler_prepare(const float* x, float* xin2, int64_t rows, int64_t c
 int b200svd_sampler_step(const float* net, const float* x, float* x_next, int64_t rows, int64_t chw, int num_frames,
                          const float* scale, float c_skip, float c_out, float sigma, float next_sigma, void* stream);
 
+/* ---- enhance stage: one DDIM step of one randomized-blending chunk (loop part) -------
+ * Replaces, per chunk and step, the guidance combine, `DDIMScheduler.step` (eta = 0; diffusers==0.30.2, restated —
+ * parity unpinned) and the blended write `latents_denoised[:, :, start+offset : start+cs] = chunk[:, :, offset:]` of
+ * code/i2v_enhance/pipeline_i2vgen_xl.py:868-903.  fp32, batch 1, layout [C][frames][hw]:
+ *   noise [cfg ? 2 : 1][C][cs][hw] (unconditional first), lat [C][lat_frames][hw] read at frames lat_start + f,
+ *   out [C][out_frames][hw] written at frames out_start + f for offset <= f < cs.
+ *   e = u + guidance (t - u);  v-prediction: x0 = sqrt(a_t) x - sqrt(1-a_t) e, eps = sqrt(a_t) e + sqrt(1-a_t) x;
+ *   epsilon: x0 = (x - sqrt(1-a_t) e) / sqrt(a_t), eps = e;  out = sqrt(a_prev) x0 + sqrt(1-a_prev) eps. */
+int b200svd_ddim_blend_step(const float* noise, const float* lat, float* out, int channels, int cs, int64_t hw,
+                            int lat_frames, int lat_start, int out_frames, int out_start, int offset, int cfg,
+                            float guidance, float alpha_t, float alpha_prev, int v_pred, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -348,9 +348,59 @@ __global__ void transpose_kernel(const __nv_bfloat16* __restrict__ in, int64_t l
   }
 }
 
+// One DDIM step (eta = 0) of one randomized-blending chunk with the classifier-free-guidance combine, written straight
+// into the blended latent (reference code/i2v_enhance/pipeline_i2vgen_xl.py:868-903; scheduler arithmetic restated
+// from diffusers==0.30.2 DDIMScheduler.step).  Layout [C][frames][hw] fp32 (batch 1).  noise: [2 or 1][C][cs][hw].
+__global__ void ddim_blend_step_kernel(const float* __restrict__ noise, const float* __restrict__ lat,
+                                       float* __restrict__ out, int64_t n, int cs, int64_t hw, int lat_frames,
+                                       int lat_start, int out_frames, int out_start, int offset, int cfg,
+                                       float guidance, float sa, float sb, float sap, float dir, int v_pred) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t px = i % hw;
+  const int f = (int)((i / hw) % cs);
+  const int64_t c = i / (hw * cs);
+  if (f < offset) return;
+  float e = noise[i];
+  if (cfg) e = e + guidance * (noise[n + i] - e);                       // uncond + g (text - uncond)
+  const float x = lat[(c * lat_frames + lat_start + f) * hw + px];
+  float x0, eps;
+  if (v_pred) {
+    x0 = sa * x - sb * e;
+    eps = sa * e + sb * x;
+  } else {
+    x0 = (x - sb * e) / sa;
+    eps = e;
+  }
+  out[(c * out_frames + out_start + f) * hw + px] = sap * x0 + dir * eps;
+}
+
 }  // namespace b200
 
 extern "C" {
+
+int b200svd_ddim_blend_step(const float* noise, const float* lat, float* out, int channels, int cs, int64_t hw,
+                            int lat_frames, int lat_start, int out_frames, int out_start, int offset, int cfg,
+                            float guidance, float alpha_t, float alpha_prev, int v_pred, void* stream) {
+  using namespace b200;
+  if (cs < 1 || offset < 0 || offset > cs || lat_start < 0 || lat_start + cs > lat_frames || out_start < 0 ||
+      out_start + cs > out_frames) {
+    set_error("ddim_blend_step: bad frame window (cs %d offset %d lat %d+%d/%d out %d+%d/%d)", cs, offset, lat_start, cs,
+              lat_frames, out_start, cs, out_frames);
+    return 1;
+  }
+  if (!(alpha_t > 0.f) || alpha_t > 1.f || alpha_prev < 0.f || alpha_prev > 1.f) {
+    set_error("ddim_blend_step: alphas_cumprod out of range");
+    return 1;
+  }
+  const int64_t n = (int64_t)channels * cs * hw;
+  if (n <= 0) return 0;
+  ddim_blend_step_kernel<<<(unsigned)((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      noise, lat, out, n, cs, hw, lat_frames, lat_start, out_frames, out_start, offset, cfg, guidance, sqrtf(alpha_t),
+      sqrtf(1.f - alpha_t), sqrtf(alpha_prev), sqrtf(1.f - alpha_prev), v_pred);
+  B200_CHECK_LAUNCH("ddim_blend_step");
+  return 0;
+}
 
 int b200svd_softmax_rows(const float* in, int64_t lds, void* out, int64_t ldo, int64_t rows, int cols, void* stream) {
   using namespace b200;

@@ -43,6 +43,15 @@ def broadcast_from_rank0(t: torch.Tensor) -> torch.Tensor:
     return t
 
 
+def broadcast_object(obj):
+    """Rank 0's picklable object on every rank (identity without a process group)."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        box = [obj]
+        dist.broadcast_object_list(box, src=0)
+        return box[0]
+    return obj
+
+
 def rank_world():
     if dist.is_available() and dist.is_initialized():
         return dist.get_rank(), dist.get_world_size()

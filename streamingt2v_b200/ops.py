@@ -488,6 +488,23 @@ def sampler_step(net, x, scale, *, num_frames, c_skip, c_out, sigma, next_sigma,
     return out
 
 
+def ddim_blend_step(noise, latents, out, *, lat_start, out_start, offset, guidance, alpha_t, alpha_prev,
+                    v_prediction=True):
+    """One DDIM step (eta = 0) + CFG combine of one randomized-blending chunk, written into `out` from frame
+    `offset` on (pipeline_i2vgen_xl.py:868-903).  noise: fp32 [2 or 1, C, cs, H, W]; latents / out: fp32 [1, C, F, H, W]
+    contiguous (they may be different tensors with different F).  guidance=None: no classifier-free guidance."""
+    for t_ in (noise, latents, out):
+        assert t_.dtype == torch.float32 and t_.is_contiguous() and t_.dim() == 5
+    nb, Cc, cs, H, W = noise.shape
+    assert nb == (1 if guidance is None else 2) and latents.shape[0] == 1 and out.shape[0] == 1
+    assert latents.shape[1] == Cc and out.shape[1] == Cc and latents.shape[3:] == (H, W) and out.shape[3:] == (H, W)
+    _call("b200svd_ddim_blend_step", _ptr(noise), _ptr(latents), _ptr(out), Cc, cs, H * W, latents.shape[2],
+          int(lat_start), out.shape[2], int(out_start), int(offset), 0 if guidance is None else 1,
+          float(guidance or 0.0), float(alpha_t), float(alpha_prev), 1 if v_prediction else 0, _stream(),
+          nbytes=4.0 * Cc * cs * H * W * (nb + 2))
+    return out
+
+
 def attention_single_head(q, k, v, n, s):
     """softmax(q k^T / sqrt(C)) v per frame, one head of width C (VAE AttnBlock).  q, k, v: contiguous [(n s), C] bf16.
     Built from the tensor-core GEMM (scores in fp32), a row-softmax kernel and a transpose."""

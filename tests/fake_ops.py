@@ -260,3 +260,19 @@ def attention_single_head(q, k, v, n, s):
         vt = transpose(v[sl])
         linear(probs, vt[None], None, out=out[sl])
     return out
+
+
+def ddim_blend_step(noise, latents, out, *, lat_start, out_start, offset, guidance, alpha_t, alpha_prev,
+                    v_prediction=True):
+    _count()
+    cs = noise.shape[2]
+    e = noise[:1] if guidance is None else noise[:1] + guidance * (noise[1:] - noise[:1])
+    x = latents[:, :, lat_start:lat_start + cs]
+    sa, sb = math.sqrt(alpha_t), math.sqrt(1.0 - alpha_t)
+    if v_prediction:
+        x0, eps = sa * x - sb * e, sa * e + sb * x
+    else:
+        x0, eps = (x - sb * e) / sa, e
+    res = math.sqrt(alpha_prev) * x0 + math.sqrt(1.0 - alpha_prev) * eps
+    out[:, :, out_start + offset:out_start + cs] = res[:, :, offset:]
+    return out
