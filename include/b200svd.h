@@ -78,6 +78,17 @@ typedef struct {
   int64_t ld2;
   float s2;
   int32_t bn; /* N tile: 32, 64, 128, 160 or 256 (0 = choose) */
+  /* optional: GroupNorm statistics of the OUTPUT taken in the epilogue (the consumer's gn_stats pass over the
+   * activation disappears; GroupNorm32, util.py:274-276).  Every 32-row quadrant of every 128-row M tile ("slot" =
+   * 4 * M-tile index + quadrant) writes, per output channel, the sum and the sum of squares over its valid rows to
+   * gn_part[slot][gn_ld][2] (fp32) and the sample index of its rows (row / gn_rows, -1 if the quadrant is empty) to
+   * gn_slot_sample[slot].  The caller guarantees that all valid rows of a quadrant belong to one sample, that the
+   * epilogue is activation-free with bf16 output (else the call fails), and reduces the partials with
+   * b200svd_gn_stats_partials.  NULL gn_part = off. */
+  float* gn_part;
+  int32_t* gn_slot_sample;
+  int64_t gn_ld;     /* channels per slot row of gn_part (>= n) */
+  uint32_t gn_rows;  /* output rows per GroupNorm sample */
 } b200svd_gemm_params;
 
 int b200svd_gemm(const b200svd_gemm_params* p, void* stream);
@@ -166,6 +177,12 @@ int b200svd_apm_mix(const float* ctx, int n, int l, int d, const float* w, const
 int b200svd_sampler_prepare(const float* x, float* xin2, int64_t rows, int64_t chw, float c_in, void* stream);
 int b200svd_sampler_step(const float* net, const float* x, float* x_next, int64_t rows, int64_t chw, int num_frames,
                          const float* scale, float c_skip, float c_out, float sigma, float next_sigma, void* stream);
+
+/* GroupNorm statistics from the epilogue partials of b200svd_gemm (see gn_part above): sums[n][32][2] doubles, the
+ * same output as b200svd_gn_stats, reduced in a fixed order (deterministic).  scratch / counters as for
+ * b200svd_gn_stats (scratch >= n * chunks * 64 doubles with chunks = ceil(n_slots / 64)). */
+int b200svd_gn_stats_partials(const float* gn_part, const int32_t* gn_slot_sample, int64_t n_slots, int64_t gn_ld,
+                              int c, int64_t n, void* sums, void* scratch, void* counters, void* stream);
 
 /* ---- enhance stage: one DDIM step of one randomized-blending chunk (loop part) -------
  * Replaces, per chunk and step, the guidance combine, `DDIMScheduler.step` (eta = 0; diffusers==0.30.2, restated —

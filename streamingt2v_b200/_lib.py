@@ -48,6 +48,10 @@ class GemmParams(C.Structure):
         ("ld2", C.c_int64),
         ("s2", C.c_float),
         ("bn", C.c_int32),
+        ("gn_part", C.c_void_p),
+        ("gn_slot_sample", C.c_void_p),
+        ("gn_ld", C.c_int64),
+        ("gn_rows", C.c_uint32),
     ]
 
 
@@ -106,6 +110,7 @@ PROTOTYPES = {
     "b200svd_apm_mix": [_P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P],
     "b200svd_sampler_prepare": [_P, _P, _I64, _I64, _F, _P],
     "b200svd_sampler_step": [_P, _P, _P, _I64, _I64, _I, _P, _F, _F, _F, _F, _P],
+    "b200svd_gn_stats_partials": [_P, _P, _I64, _I64, _I, _I64, _P, _P, _P, _P],
     "b200svd_ddim_blend_step": [_P, _P, _P, _I, _I, _I64, _I, _I, _I, _I, _I, _I, _F, _F, _F, _I, _P],
 }
 

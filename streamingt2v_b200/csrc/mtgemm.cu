@@ -63,6 +63,10 @@ struct GemmDev {
   const __nv_bfloat16* res2;
   int64_t ld2;
   float s2;
+  float* gn_part;           // GroupNorm partial sums of the output (EPI == 2 only), see b200svd.h
+  int32_t* gn_slot_sample;
+  int64_t gn_ld;
+  uint32_t gn_rows;
 };
 
 constexpr int BM = 128;
@@ -96,6 +100,9 @@ struct TileCfg {
 
 // `tile` enumerates (N tile fastest, then M tile) — in PAIR mode (M-tile PAIR); mrank selects this CTA's M tile of the
 // pair.  An M tile index past the end decodes to coordinates beyond the extents (all rows out of bounds).
+__device__ __forceinline__ uint32_t m_tile_index(const GemmDev& p, uint32_t tile, uint32_t mmul, uint32_t mrank) {
+  return (tile / p.n_tiles) * mmul + mrank;
+}
 __device__ __forceinline__ void decode_tile(const GemmDev& p, uint32_t tile, uint32_t mmul, uint32_t mrank,
                                             uint32_t nmul, uint32_t nrank, uint32_t& n_tile, uint32_t& mb1,
                                             uint32_t& mb2, uint32_t& mb3) {
@@ -520,7 +527,44 @@ mtgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
               }
               *reinterpret_cast<uint4*>(orow + ((c_lo ^ x) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
               *reinterpret_cast<uint4*>(orow + ((c_hi ^ x) << 4)) = make_uint4(o[4], o[5], o[6], o[7]);
+              if (p.gn_part != nullptr && inb) {
+                // per-column sum / sum of squares over the 32 rows of this quadrant (of the bf16-ROUNDED values, the
+                // ones the consumer reads): 32-lane transpose-reduce, 16 + 16 shuffles; lane L ends with column
+                // (L >> 1) & 15, even lanes store 16 x (sum, sumsq) = 128 contiguous bytes
+                float a[16], b[16];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float lo = valid ? bf16_lo(o[j]) : 0.f, hi = valid ? bf16_hi(o[j]) : 0.f;
+                  a[2 * j] = lo;
+                  a[2 * j + 1] = hi;
+                  b[2 * j] = lo * lo;
+                  b[2 * j + 1] = hi * hi;
+                }
+#pragma unroll
+                for (int w = 8, bit = 16; w >= 1; w >>= 1, bit >>= 1) {
+                  const bool up = (lane & bit) != 0;
+#pragma unroll
+                  for (int i = 0; i < w; ++i) {
+                    const float keep_a = up ? a[w + i] : a[i], send_a = up ? a[i] : a[w + i];
+                    const float keep_b = up ? b[w + i] : b[i], send_b = up ? b[i] : b[w + i];
+                    a[i] = keep_a + __shfl_xor_sync(0xffffffffu, send_a, bit);
+                    b[i] = keep_b + __shfl_xor_sync(0xffffffffu, send_b, bit);
+                  }
+                }
+                a[0] += __shfl_xor_sync(0xffffffffu, a[0], 1);
+                b[0] += __shfl_xor_sync(0xffffffffu, b[0], 1);
+                if ((lane & 1) == 0) {
+                  const uint32_t slot = m_tile_index(p, tile_begin + tcount, PAIR ? 2u : 1u, rank) * 4u + (uint32_t)q;
+                  float2* dst = reinterpret_cast<float2*>(p.gn_part) + (int64_t)slot * p.gn_ld + ocol + ((lane >> 1) & 15);
+                  *dst = make_float2(a[0], b[0]);
+                }
+              }
             }
+          }
+          if (p.gn_part != nullptr && lane == 0 && n_tile == 0 && s == 0) {
+            // lane 0 owns the first row of the quadrant: if it is out of range, so is every row of the quadrant
+            const uint32_t slot = m_tile_index(p, tile_begin + tcount, PAIR ? 2u : 1u, rank) * 4u + (uint32_t)q;
+            p.gn_slot_sample[slot] = valid ? (int32_t)((uint32_t)row / p.gn_rows) : -1;
           }
           fence_proxy_async_smem();
         }
@@ -899,6 +943,10 @@ extern "C" int b200svd_gemm(const b200svd_gemm_params* p, void* stream) {
   d.res2 = reinterpret_cast<const __nv_bfloat16*>(p->res2);
   d.ld2 = p->ld2;
   d.s2 = p->s2;
+  d.gn_part = p->gn_part;
+  d.gn_slot_sample = p->gn_slot_sample;
+  d.gn_ld = p->gn_ld;
+  d.gn_rows = p->gn_rows ? p->gn_rows : 1;
 
   int bn = p->bn;
   if (p->act == B200SVD_ACT_GEGLU) {
@@ -952,6 +1000,12 @@ extern "C" int b200svd_gemm(const b200svd_gemm_params* p, void* stream) {
   const bool lean = lean_epi && p->act == B200SVD_ACT_NONE && d.tma_epi && (n_out_h % 16) == 0 &&
                     (p->bias == nullptr || al16(p->bias)) &&
                     (p->fvec == nullptr || (al16(p->fvec) && (p->ldf % 4) == 0)) && !quad;
+  if (p->gn_part != nullptr && (!lean || bn < 128 || p->gn_slot_sample == nullptr || p->gn_ld < (int64_t)p->n ||
+                                 (p->gn_ld % 2) != 0 || (reinterpret_cast<uintptr_t>(p->gn_part) & 7) != 0)) {
+    set_error("b200svd_gemm: gn_part needs the activation-free bf16 epilogue (n %% 16 == 0, n > 64), gn_slot_sample and "
+              "an 8-byte aligned partial buffer with gn_ld >= n");
+    return 1;
+  }
   if (lean) {
     switch (bn) {
       case 128: return pair ? launch<128, 2, 2>(p, tmA, d, st) : launch<128, 1, 2>(p, tmA, d, st);

@@ -130,6 +130,89 @@ __global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// GroupNorm statistics from the per-quadrant partials written by the GEMM epilogue (mtgemm.cu, gn_part):
+// part [n_slots][ld][2] fp32 (sum, sum of squares per channel over the <= 32 rows of a slot), slot_sample [n_slots].
+// grid = (chunks of 64 slots, N); the block adds the slots of ITS sample in slot order (fixed), folds channels into
+// groups in double, and the last block of the sample (ticket) adds the chunk partials in chunk order: deterministic.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int GNP_SLOTS = 64;
+constexpr int GNP_THREADS = 256;
+__global__ void __launch_bounds__(GNP_THREADS)
+gn_stats_partials_kernel(const float2* __restrict__ part, const int* __restrict__ slot_sample, int64_t n_slots,
+                         int64_t ld, int C, double* __restrict__ sums, double* __restrict__ partial,
+                         int* __restrict__ counters) {
+  extern __shared__ float sm[];  // [2][C], reused as doubles by the last block
+  __shared__ int is_last;
+  __shared__ int hit[GNP_SLOTS];
+  const int n = blockIdx.y;
+  const int chunks = gridDim.x;
+  const int64_t s0 = (int64_t)blockIdx.x * GNP_SLOTS;
+  if (threadIdx.x < GNP_SLOTS) {
+    const int64_t sl = s0 + threadIdx.x;
+    hit[threadIdx.x] = (sl < n_slots && slot_sample[sl] == n) ? 1 : 0;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += GNP_THREADS) {
+    float a = 0.f, b = 0.f;
+    for (int i = 0; i < GNP_SLOTS; ++i) {
+      if (hit[i]) {
+        const float2 v = __ldg(part + (s0 + i) * ld + c);
+        a += v.x;
+        b += v.y;
+      }
+    }
+    sm[c] = a;
+    sm[C + c] = b;
+  }
+  __syncthreads();
+  const int cpg = C >> 5;
+  if (threadIdx.x < 64) {
+    const int g = threadIdx.x & 31, which = threadIdx.x >> 5;
+    double a = 0.0;
+    for (int j = 0; j < cpg; ++j) a += (double)sm[which * C + g * cpg + j];
+    partial[(((int64_t)n * chunks + blockIdx.x) * 32 + g) * 2 + which] = a;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int ticket = atomicAdd(&counters[n], 1);
+    is_last = (ticket == chunks - 1);
+    if (is_last) counters[n] = 0;
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    const int pairs = 64;
+    const int parts = GNP_THREADS / pairs;  // 4
+    double* dsm = reinterpret_cast<double*>(sm);  // parts * 64 doubles = 2 KB <= 2 * C floats (C >= 256) — checked on host
+    const int pr = threadIdx.x % pairs, part_i = threadIdx.x / pairs;
+    const double* src = partial + (int64_t)n * chunks * 64 + (pr & 31) * 2 + (pr >> 5);
+    constexpr int W = 8;
+    double a[W];
+#pragma unroll
+    for (int i = 0; i < W; ++i) a[i] = 0.0;
+    int c = part_i;
+    for (; c + (W - 1) * parts < chunks; c += W * parts) {
+#pragma unroll
+      for (int i = 0; i < W; ++i) a[i] += src[(int64_t)(c + i * parts) * 64];
+    }
+    for (; c < chunks; c += parts) a[0] += src[(int64_t)c * 64];
+#pragma unroll
+    for (int w = W / 2; w > 0; w >>= 1)
+#pragma unroll
+      for (int i = 0; i < w; ++i) a[i] += a[i + w];
+    __syncthreads();
+    dsm[part_i * pairs + pr] = a[0];
+    __syncthreads();
+    if (threadIdx.x < pairs) {
+      double t = 0.0;
+      for (int q = 0; q < parts; ++q) t += dsm[q * pairs + threadIdx.x];
+      sums[((int64_t)n * 32 + (threadIdx.x & 31)) * 2 + (threadIdx.x >> 5)] = t;
+    }
+  }
+}
+
 // y = [silu]((x - mean) * rstd * gamma + beta), bf16 out (row stride ldy).
 __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, __nv_bfloat16* __restrict__ y,
                                 int64_t ldy, int P, int C, int rows_per_chunk, const double* __restrict__ sums,
@@ -458,6 +541,30 @@ int64_t b200svd_gn_scratch_doubles(int64_t n, int64_t p, int c) {
   int threads, rpc, chunks;
   if (gn_geometry(c, n, (int)p, &threads, &rpc, &chunks)) return -1;
   return n * (int64_t)chunks * 64;
+}
+
+int b200svd_gn_stats_partials(const float* gn_part, const int32_t* gn_slot_sample, int64_t n_slots, int64_t gn_ld,
+                              int c, int64_t n, void* sums, void* scratch, void* counters, void* stream) {
+  using namespace b200;
+  if (c % 32 != 0 || c < 256 || c > 8192 || gn_ld < c || n_slots < 1 || n < 1) {
+    set_error("gn_stats_partials: need 256 <= c <= 8192, c %% 32 == 0, gn_ld >= c (c %d, ld %lld, slots %lld)", c,
+              (long long)gn_ld, (long long)n_slots);
+    return 1;
+  }
+  const int64_t chunks = (n_slots + GNP_SLOTS - 1) / GNP_SLOTS;
+  dim3 grid((unsigned)chunks, (unsigned)n);
+  const size_t smem = (size_t)2 * c * sizeof(float);
+  static size_t smem_set = 0;
+  if (smem > 48 * 1024 && smem > smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(gn_stats_partials_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(gn_stats_partials)");
+    smem_set = smem;
+  }
+  gn_stats_partials_kernel<<<grid, GNP_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float2*>(gn_part), gn_slot_sample, n_slots, gn_ld, c, reinterpret_cast<double*>(sums),
+      reinterpret_cast<double*>(scratch), reinterpret_cast<int*>(counters));
+  B200_CHECK_LAUNCH("gn_stats_partials");
+  return 0;
 }
 
 int b200svd_gn_stats(const void* x, int64_t ldx, int64_t n, int64_t p, int c, void* sums, void* scratch,

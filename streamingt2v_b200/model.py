@@ -245,13 +245,16 @@ class B200Denoiser:
         a, b_ = W.emb_slices[layer.prefix + "/t"]
         e2 = emb_all[:, a:b_]
         g1 = ops.group_norm(x, n, S, d["gn1"][0], d["gn1"][1], 1e-5, silu=True)
-        h1 = ops.conv3x3(g1.view(n, h, w, cin), d["conv1"][0], d["conv1"][1], fvec=e1, rows_per_frame=S)
+        # gn_rows: the GEMM epilogue leaves the GroupNorm statistics of its output (per frame / per video) as
+        # per-quadrant partial sums, so the following group_norm does not read the activation for its statistics
+        h1 = ops.conv3x3(g1.view(n, h, w, cin), d["conv1"][0], d["conv1"][1], fvec=e1, rows_per_frame=S, gn_rows=S)
         g2 = ops.group_norm(h1, n, S, d["gn2"][0], d["gn2"][1], 1e-5, silu=True)
         xs = x if d["skip"] is None else ops.linear(x, d["skip"][0], d["skip"][1])
-        x_s = ops.conv3x3(g2.view(n, h, w, cout), d["conv2"][0], d["conv2"][1], res1=xs, s1=1.0)
+        x_s = ops.conv3x3(g2.view(n, h, w, cout), d["conv2"][0], d["conv2"][1], res1=xs, s1=1.0, gn_rows=T * S)
         # time_stack: ResBlock(dims=3) on [b, c, t, h, w]; its GroupNorm reduces over (c/32, t, h, w) per batch
         g3 = ops.group_norm(x_s, B, T * S, d["gn3"][0], d["gn3"][1], 1e-5, silu=True)
-        h3 = ops.tconv3(g3.view(B, T, S, cout), d["tconv1"][0], d["tconv1"][1], fvec=e2, rows_per_frame=S)
+        h3 = ops.tconv3(g3.view(B, T, S, cout), d["tconv1"][0], d["tconv1"][1], fvec=e2, rows_per_frame=S,
+                        gn_rows=T * S)
         g4 = ops.group_norm(h3, B, T * S, d["gn4"][0], d["gn4"][1], 1e-5, silu=True)
         # x_t = x_s + conv(..) ; blend = a*x_s + (1-a)*x_t = x_s + (1-a)*conv(..)
         return ops.tconv3(g4.view(B, T, S, cout), d["tconv2"][0], d["tconv2"][1], s_acc=1.0 - d["alpha"], res1=x_s,

@@ -7,6 +7,7 @@ from __future__ import annotations
 
 import ctypes as C
 import itertools
+import os
 from functools import lru_cache
 
 import torch
@@ -116,7 +117,7 @@ def pick_box(e1: int, e2: int, e3: int):
 
 def gemm_raw(*, a, a_dims, a_strides, a_box, w, n, k, taps, tap_off, m_ext, m_box, m_adim, out, ldo, out_rs=None,
              out_fp32=False, bias=None, fvec=None, ldf=0, rows_per_frame=1, act=ACT_NONE, s_acc=1.0, res1=None,
-             ld1=0, s1=1.0, res2=None, ld2=0, s2=1.0, bn=0):
+             ld1=0, s1=1.0, res2=None, ld2=0, s2=1.0, bn=0, gn=None):
     global _launch_count
     p = GemmParams()
     p.a_ptr = a.data_ptr()
@@ -153,6 +154,11 @@ def gemm_raw(*, a, a_dims, a_strides, a_box, w, n, k, taps, tap_off, m_ext, m_bo
     p.ld2 = int(ld2)
     p.s2 = float(s2)
     p.bn = int(bn)
+    if gn is not None:
+        p.gn_part = gn["part"].data_ptr()
+        p.gn_slot_sample = gn["slot"].data_ptr()
+        p.gn_ld = int(gn["C"])
+        p.gn_rows = int(gn["p"])
     lib = _lib.load()
     e0 = _prof_begin()
     _lib.check(lib.b200svd_gemm(C.byref(p), _stream()), "b200svd_gemm")
@@ -165,6 +171,48 @@ def gemm_raw(*, a, a_dims, a_strides, a_box, w, n, k, taps, tap_off, m_ext, m_bo
         desc = (f"M{rows} K{k} N{n} taps{taps} act{act} res{(res1 is not None) + (res2 is not None)} "
                 f"fvec{int(fvec is not None)} f32{int(out_fp32)} box{tuple(int(b) for b in m_box)}")
         _prof_end(e0, ("mtgemm", desc), 2.0 * rows * k * n * taps, nbytes)
+
+
+GN_FUSE = os.environ.get("B200SVD_GN_FUSE", "1") != "0"
+
+
+@lru_cache(maxsize=None)
+def _gn_slots(m_ext, m_box, p):
+    """Number of (M tile, quadrant) slots of a GEMM launch if every 32-row quadrant of every 128-row tile lies inside
+    ONE GroupNorm sample of p consecutive output rows (then the epilogue can take the statistics), else 0."""
+    import numpy as np
+    (e1, e2, e3), (b1, b2, b3) = m_ext, m_box
+    t1, t2, t3 = -(-e1 // b1), -(-e2 // b2), -(-e3 // b3)
+    c1 = min(b1, 32)
+    c2 = min(b2, 32 // c1)
+    c3 = 32 // (c1 * c2)
+    i1, i2, i3, q = np.meshgrid(np.arange(t1), np.arange(t2), np.arange(t3), np.arange(4), indexing="ij")
+    qoff = q * 32
+    a1 = i1 * b1 + qoff % b1
+    a2 = i2 * b2 + (qoff // b1) % b2
+    a3 = i3 * b3 + qoff // (b1 * b2)
+    ok = (a1 < e1) & (a2 < e2) & (a3 < e3)                      # quadrants with at least one valid row
+    z1 = np.minimum(a1 + c1, e1) - 1
+    z2 = np.minimum(a2 + c2, e2) - 1
+    z3 = np.minimum(a3 + c3, e3) - 1
+    lo = a1 + a2 * e1 + a3 * e1 * e2
+    hi = z1 + z2 * e1 + z3 * e1 * e2
+    if bool(((lo // p != hi // p) & ok).any()):
+        return 0
+    m_tiles = t1 * t2 * t3
+    return (m_tiles + (m_tiles & 1)) * 4                         # pair tiles may decode one M tile past the end
+
+
+def _gn_request(gn_rows, m_ext, m_box, n_out, act, out_fp32, device):
+    """Partial-statistics buffers for a launch whose output feeds a GroupNorm over samples of gn_rows rows, or None."""
+    if gn_rows is None or not GN_FUSE or act != ACT_NONE or out_fp32 or n_out % 32 or n_out < 256:
+        return None
+    n_slots = _gn_slots(tuple(int(v) for v in m_ext), tuple(int(v) for v in m_box), int(gn_rows))
+    if n_slots == 0:
+        return None
+    return dict(part=torch.empty((n_slots, n_out, 2), dtype=torch.float32, device=device),
+                slot=torch.empty((n_slots,), dtype=torch.int32, device=device), n_slots=n_slots, p=int(gn_rows),
+                C=int(n_out))
 
 
 def _epi_kwargs(rows, n_out, out, bias, fvec, rows_per_frame, act, s_acc, res1, s1, res2, s2, out_fp32):
@@ -189,7 +237,7 @@ def _alloc_out(rows, n_out, out, out_fp32, device):
 
 
 def linear(x, w, bias=None, *, act=ACT_NONE, out=None, out_fp32=False, fvec=None, rows_per_frame=1, s_acc=1.0,
-           res1=None, s1=1.0, res2=None, s2=1.0, bn=0):
+           res1=None, s1=1.0, res2=None, s2=1.0, bn=0, gn_rows=None):
     """x: [M, K] bf16 (row stride arbitrary, multiple of 8); w: packed [1, N, K] bf16; returns [M, N_out]."""
     assert x.dtype == torch.bfloat16 and x.dim() == 2 and x.stride(1) == 1
     M, K = x.shape
@@ -199,10 +247,13 @@ def linear(x, w, bias=None, *, act=ACT_NONE, out=None, out_fp32=False, fvec=None
     out = _alloc_out(M, n_out, out, out_fp32, x.device)
     ld = x.stride(0)
     big = ld * 2 * max(M, 1)
+    gn = _gn_request(gn_rows, (M, 1, 1), (128, 1, 1), n_out, act, out_fp32, x.device)
     gemm_raw(a=x, a_dims=(K, M, 1, 1, 1), a_strides=(ld * 2, big, big, big), a_box=(64, 128, 1, 1, 1),
              w=w, n=N, k=K, taps=1, tap_off=[(0, 0, 0, 0, 0)], m_ext=(M, 1, 1), m_box=(128, 1, 1),
-             m_adim=(1, 2, 3), out=out, ldo=out.stride(0), bn=bn,
+             m_adim=(1, 2, 3), out=out, ldo=out.stride(0), bn=bn, gn=gn,
              **_epi_kwargs(M, n_out, out, bias, fvec, rows_per_frame, act, s_acc, res1, s1, res2, s2, out_fp32))
+    if gn is not None:
+        out._b200_gn = gn          # consumed by group_norm(out, ...) instead of a statistics pass over `out`
     return out
 
 
@@ -263,9 +314,12 @@ def _conv_common(x, a_dims, a_strides, a_box, w, Cout, K, taps, m_ext, m_box, m_
     kw = _epi_kwargs(rows, n_out, out, bias, epi.pop("fvec", None), epi.pop("rows_per_frame", 1), act,
                      epi.pop("s_acc", 1.0), epi.pop("res1", None), epi.pop("s1", 1.0), epi.pop("res2", None),
                      epi.pop("s2", 1.0), out_fp32)
+    gn = _gn_request(epi.pop("gn_rows", None), m_ext, m_box, n_out, act, out_fp32, x.device)
     assert not epi, f"unknown epilogue args {list(epi)}"
     gemm_raw(a=x, a_dims=a_dims, a_strides=a_strides, a_box=a_box, w=w, n=Cout, k=K, taps=len(taps), tap_off=taps,
-             m_ext=m_ext, m_box=m_box, m_adim=m_adim, out=out, ldo=out.stride(0), bn=bn, **kw)
+             m_ext=m_ext, m_box=m_box, m_adim=m_adim, out=out, ldo=out.stride(0), bn=bn, gn=gn, **kw)
+    if gn is not None:
+        out._b200_gn = gn
     return out
 
 
@@ -273,6 +327,7 @@ def _conv_common(x, a_dims, a_strides, a_box, w, Cout, K, taps, m_ext, m_box, m_
 # attention
 # ----------------------------------------------------------------------------------------------------------------
 _FAMILY = {"b200svd_flash_attn": "flash_attn", "b200svd_small_attn": "small_attn", "b200svd_pixel_attn": "pixel_attn", "b200svd_gn_stats": "groupnorm",
+           "b200svd_gn_stats_partials": "groupnorm",
            "b200svd_gn_apply": "groupnorm", "b200svd_layernorm": "layernorm"}
 
 
@@ -352,12 +407,21 @@ def group_norm(x, n, p, gamma, beta, eps, *, silu=False, out=None, sums=None):
         sums = torch.empty((n, 32, 2), dtype=torch.float64, device=x.device)
     if out is None:
         out = torch.empty((n * p, Cc), dtype=torch.bfloat16, device=x.device)
-    need = _lib.load().b200svd_gn_scratch_doubles(n, p, Cc)
-    if need < 0:
-        raise _lib.B200Error(f"group_norm: unsupported channel count {Cc}")
-    scratch, counters = _gn_scratch(x.device, need, n)
-    _call("b200svd_gn_stats", _ptr(x), x.stride(0), n, p, Cc, _ptr(sums), _ptr(scratch), _ptr(counters), _stream(),
-          nbytes=2.0 * n * p * Cc, desc=f"stats n{n} p{p} c{Cc}")
+    gn = getattr(x, "_b200_gn", None)
+    if gn is not None and gn["p"] == p and gn["C"] == Cc and x.stride(0) == Cc:
+        # the producing GEMM left per-quadrant partial sums: reduce those (12.5 % of the bytes) instead of reading x
+        chunks = -(-gn["n_slots"] // 64)
+        scratch, counters = _gn_scratch(x.device, n * chunks * 64, n)
+        _call("b200svd_gn_stats_partials", _ptr(gn["part"]), _ptr(gn["slot"]), gn["n_slots"], Cc, Cc, n, _ptr(sums),
+              _ptr(scratch), _ptr(counters), _stream(), nbytes=8.0 * gn["n_slots"] * Cc,
+              desc=f"stats(partials) n{n} p{p} c{Cc}")
+    else:
+        need = _lib.load().b200svd_gn_scratch_doubles(n, p, Cc)
+        if need < 0:
+            raise _lib.B200Error(f"group_norm: unsupported channel count {Cc}")
+        scratch, counters = _gn_scratch(x.device, need, n)
+        _call("b200svd_gn_stats", _ptr(x), x.stride(0), n, p, Cc, _ptr(sums), _ptr(scratch), _ptr(counters), _stream(),
+              nbytes=2.0 * n * p * Cc, desc=f"stats n{n} p{p} c{Cc}")
     _call("b200svd_gn_apply", _ptr(x), x.stride(0), _ptr(out), out.stride(0), n, p, Cc, _ptr(sums), _ptr(gamma),
           _ptr(beta), float(eps), 1 if silu else 0, _stream(), nbytes=4.0 * n * p * Cc, desc=f"apply n{n} p{p} c{Cc}")
     return out

@@ -60,12 +60,12 @@ class B200VaeDecoder:
         e = self.w[p]
         S, B = h * w, n // T
         g1 = ops.group_norm(x, n, S, e["gn1"][0], e["gn1"][1], 1e-6, silu=True)
-        h1 = ops.conv3x3(g1.view(n, h, w, cin), e["conv1"][0], e["conv1"][1])
+        h1 = ops.conv3x3(g1.view(n, h, w, cin), e["conv1"][0], e["conv1"][1], gn_rows=S)
         g2 = ops.group_norm(h1, n, S, e["gn2"][0], e["gn2"][1], 1e-6, silu=True)
         xs = x if e["skip"] is None else ops.linear(x, e["skip"][0], e["skip"][1])
-        x_s = ops.conv3x3(g2.view(n, h, w, cout), e["conv2"][0], e["conv2"][1], res1=xs, s1=1.0)
+        x_s = ops.conv3x3(g2.view(n, h, w, cout), e["conv2"][0], e["conv2"][1], res1=xs, s1=1.0, gn_rows=T * S)
         g3 = ops.group_norm(x_s, B, T * S, e["gn3"][0], e["gn3"][1], 1e-5, silu=True)
-        h3 = ops.tconv3(g3.view(B, T, S, cout), e["tconv1"][0], e["tconv1"][1])
+        h3 = ops.tconv3(g3.view(B, T, S, cout), e["tconv1"][0], e["tconv1"][1], gn_rows=T * S)
         g4 = ops.group_norm(h3, B, T * S, e["gn4"][0], e["gn4"][1], 1e-5, silu=True)
         return ops.tconv3(g4.view(B, T, S, cout), e["tconv2"][0], e["tconv2"][1], s_acc=e["alpha"], res1=x_s, s1=1.0)
 

@@ -55,7 +55,7 @@ def _epilogue(v, rows, *, bias, act, fvec, rows_per_frame, s_acc, res1, s1, res2
 
 
 def linear(x, w, bias=None, *, act=ACT_NONE, out=None, out_fp32=False, fvec=None, rows_per_frame=1, s_acc=1.0,
-           res1=None, s1=1.0, res2=None, s2=1.0, bn=0):
+           res1=None, s1=1.0, res2=None, s2=1.0, bn=0, gn_rows=None):
     assert x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and w.dim() == 3 and w.shape[0] == 1
     v = x.float() @ w[0].float().t()
     return _epilogue(v, x.shape[0], bias=bias, act=act, fvec=fvec, rows_per_frame=rows_per_frame, s_acc=s_acc,

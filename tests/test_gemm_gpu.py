@@ -143,3 +143,51 @@ def test_tconv3(cuda_dev, B, T, P, C):
     ref = F.conv3d(x5, w.float(), b, padding=(1, 0, 0))[..., 0].permute(0, 2, 3, 1).reshape(-1, C)
     ref = 0.4 * ref + r1.float()
     _check(out, ref, f"tconv3 B{B} T{T} P{P} C{C}")
+
+
+@pytest.mark.parametrize("kind,shape,p_rows", [("conv", (6, 24, 64, 320), "frame"), ("conv", (4, 36, 64, 640), "video"),
+                                                 ("tconv", (2, 5, 640, 320), "video"), ("linear", (4096, 320), 512),
+                                                 ("conv", (3, 24, 40, 320), "frame")])
+def test_groupnorm_statistics_from_the_gemm_epilogue(cuda_dev, kind, shape, p_rows):
+    """gn_rows: the GEMM epilogue leaves per-quadrant partial sums of its (bf16-rounded) output and group_norm reduces
+    those instead of reading the activation.  Must agree with the statistics pass over the stored tensor."""
+    from streamingt2v_b200 import ops, packing
+    g = torch.Generator().manual_seed(1)
+    if kind == "conv":
+        N, H, W, Cc = shape
+        x = (torch.randn(shape, generator=g) * 1.3 + 0.2).to(cuda_dev).to(torch.bfloat16)
+        wt = packing.pack_conv3x3(torch.randn(Cc, Cc, 3, 3, generator=g) * (9 * Cc) ** -0.5, cuda_dev)
+        n, p = (N, H * W) if p_rows == "frame" else (1, N * H * W)
+        run = lambda **kw: ops.conv3x3(x, wt, None, **kw)  # noqa: E731
+    elif kind == "tconv":
+        B, T, P, Cc = shape
+        x = (torch.randn(shape, generator=g) * 1.3 + 0.2).to(cuda_dev).to(torch.bfloat16)
+        wt = packing.pack_tconv3(torch.randn(Cc, Cc, 3, 1, 1, generator=g) * (3 * Cc) ** -0.5, cuda_dev)
+        n, p = B, T * P
+        run = lambda **kw: ops.tconv3(x, wt, None, **kw)  # noqa: E731
+    else:
+        M, Cc = shape
+        x = (torch.randn(shape, generator=g) * 1.3 + 0.2).to(cuda_dev).to(torch.bfloat16)
+        wt = packing.pack_linear(torch.randn(Cc, Cc, generator=g) * Cc ** -0.5, cuda_dev)
+        n, p = M // p_rows, p_rows
+        run = lambda **kw: ops.linear(x, wt, None, **kw)  # noqa: E731
+    gamma = torch.randn(Cc, device=cuda_dev) * 0.2 + 1.0
+    beta = torch.randn(Cc, device=cuda_dev) * 0.2
+    y = run(gn_rows=p)
+    assert getattr(y, "_b200_gn", None) is not None, "launch geometry was expected to be fusable"
+    y_plain = run()
+    assert torch.equal(y, y_plain)                                 # the GEMM result itself is unchanged
+    sums_f = torch.empty((n, 32, 2), dtype=torch.float64, device=cuda_dev)
+    sums_p = torch.empty((n, 32, 2), dtype=torch.float64, device=cuda_dev)
+    out_f = ops.group_norm(y, n, p, gamma, beta, 1e-5, silu=True, sums=sums_f)
+    out_p = ops.group_norm(y_plain, n, p, gamma, beta, 1e-5, silu=True, sums=sums_p)
+    torch.cuda.synchronize()
+    rel = ((sums_f - sums_p).abs() / sums_p.abs().clamp_min(1e-3)).max().item()
+    print(f"gn partials {kind} {shape}: max rel diff of the group sums {rel:.3e}")
+    assert rel < 1e-5
+    assert (out_f.float() - out_p.float()).abs().max().item() <= 2e-2
+    # deterministic
+    y2 = run(gn_rows=p)
+    s2 = torch.empty_like(sums_f)
+    ops.group_norm(y2, n, p, gamma, beta, 1e-5, silu=True, sums=s2)
+    assert torch.equal(s2, sums_f)
