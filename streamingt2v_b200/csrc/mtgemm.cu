@@ -85,8 +85,16 @@ struct TileCfg {
   static constexpr int B_ROWS = PAIR ? BN / 2 : BN;
   static constexpr int B_STAGE_BYTES = B_ROWS * BK * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int ACC_STRIDE = (BN <= 32) ? 32 : (BN <= 64) ? 64 : (BN <= 128) ? 128 : 256;
-  static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
+  // BN = 320 (pair tiles only): every layer width of the network is a multiple of 320, so there is no ragged N tile,
+  // and the tile has the fewest bytes into the SM per FLOP (36 KB per 128x320x64 MACs).  tcgen05.mma takes N <= 256:
+  // two MMAs of N = 160 per k step, each CTA stages two 80-row pieces of B.  320 fp32 columns fit TMEM only once, so the
+  // accumulator is single-buffered (the epilogue of tile i is exposed) — used where the main loop is long.
+  static constexpr int NMMA = (BN > 256) ? 2 : 1;
+  static constexpr int BN_MMA = BN / NMMA;
+  static constexpr int NBUF = (BN > 256) ? 1 : 2;
+  static constexpr int ACC_STRIDE = (BN <= 32) ? 32 : (BN <= 64) ? 64 : (BN <= 128) ? 128 : (BN <= 256) ? 256 : 512;
+  static constexpr int TMEM_COLS = NBUF * ACC_STRIDE;
+  static_assert(BN <= 256 || PAIR, "the 320-wide tile exists as a 2-SM tile only");
   static constexpr int NSUB = (BN + 63) / 64;
   static constexpr int OUT_BYTES = EPI_WARPS * OUT_BUF_BYTES;  // one private 32-row x 64-column staging block per warp
   static constexpr int FIXED_BYTES = OUT_BYTES + 512;
@@ -226,8 +234,10 @@ mtgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
               } else {
                 tma_load_5d_2sm(sa, &tmA, &full_bar[s], c0 + (int)(kb * BK), c1, c2, c3, c4);
               }
-              tma_load_3d_2sm(sa + A_STAGE_BYTES, &tmB, &full_bar[s], (int)(kb * BK), n0 + (int)(rank * (BN / 2)),
-                              (int)tap);
+#pragma unroll
+              for (int hh = 0; hh < Cfg::NMMA; ++hh)
+                tma_load_3d_2sm(sa + A_STAGE_BYTES + hh * (Cfg::BN_MMA / 2) * 128, &tmB, &full_bar[s], (int)(kb * BK),
+                                n0 + hh * Cfg::BN_MMA + (int)(rank * (Cfg::BN_MMA / 2)), (int)tap);
             } else {
               mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
               tma_load_5d(sa, &tmA, &full_bar[s], c0 + (int)(kb * BK), c1, c2, c3, c4);
@@ -240,11 +250,12 @@ mtgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   } else if (warp == 1) {
     if (lane == 0 && rank == 0) {
       // ===================== MMA issuer (leader CTA only in PAIR mode) =====================
-      constexpr uint32_t idesc = make_idesc_f16(PAIR ? 2 * BM : BM, BN, /*bf16*/ 1, 0, 0);
+      constexpr uint32_t idesc = make_idesc_f16(PAIR ? 2 * BM : BM, Cfg::BN_MMA, /*bf16*/ 1, 0, 0);
       uint32_t it = 0, tcount = 0;
       for (uint32_t tile = tile_begin; tile < tile_end; ++tile, ++tcount) {
-        const uint32_t b = tcount & 1;
-        mbar_wait_parked(&acc_empty[b], ((tcount >> 1) & 1) ^ 1);  // epilogue has drained this accumulator buffer
+        const uint32_t b = Cfg::NBUF == 2 ? (tcount & 1) : 0u;
+        const uint32_t bpar = Cfg::NBUF == 2 ? ((tcount >> 1) & 1) : (tcount & 1);
+        mbar_wait_parked(&acc_empty[b], bpar ^ 1);  // epilogue has drained this accumulator buffer
         tc_fence_after();
         const uint32_t tacc = tmem_base + b * Cfg::ACC_STRIDE;
         for (uint32_t i = 0; i < iters_per_tile; ++i, ++it) {
@@ -254,14 +265,18 @@ mtgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + s * Cfg::STAGE_BYTES);
           const uint64_t adesc = smem_desc_k_sw128(sa);
-          const uint64_t bdesc = smem_desc_k_sw128(sa + A_STAGE_BYTES);
 #pragma unroll
-          for (int kk = 0; kk < BK / 16; ++kk) {
-            // advance 16 elements (32 B) along K inside the 128B swizzle atom: +2 in the (addr>>4) field
-            if (PAIR)
-              umma_f16_ss_2sm(tacc, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, (i > 0 || kk > 0) ? 1u : 0u);
-            else
-              umma_f16_ss(tacc, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, (i > 0 || kk > 0) ? 1u : 0u);
+          for (int hh = 0; hh < Cfg::NMMA; ++hh) {
+            const uint64_t bdesc = smem_desc_k_sw128(sa + A_STAGE_BYTES + hh * (PAIR ? Cfg::BN_MMA / 2 : Cfg::BN_MMA) * 128);
+            const uint32_t tacc_h = tacc + (uint32_t)(hh * Cfg::BN_MMA);
+#pragma unroll
+            for (int kk = 0; kk < BK / 16; ++kk) {
+              // advance 16 elements (32 B) along K inside the 128B swizzle atom: +2 in the (addr>>4) field
+              if (PAIR)
+                umma_f16_ss_2sm(tacc_h, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, (i > 0 || kk > 0) ? 1u : 0u);
+              else
+                umma_f16_ss(tacc_h, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, (i > 0 || kk > 0) ? 1u : 0u);
+            }
           }
           // frees the smem stage (in both CTAs of a pair) once these MMAs have read it
           if (QUAD) umma_commit_2sm(&empty_bar[s], (uint16_t)0xF);
@@ -297,6 +312,8 @@ mtgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     const bool fvec_vec = p.fvec != nullptr && (reinterpret_cast<uintptr_t>(p.fvec) & 15) == 0 && (p.ldf & 3) == 0;
     const uint32_t num_tiles = tile_end > tile_begin ? tile_end - tile_begin : 0u;
 
+    auto acc_buf = [](uint32_t t) -> uint32_t { return Cfg::NBUF == 2 ? (t & 1u) : 0u; };
+    auto acc_par = [](uint32_t t) -> uint32_t { return Cfg::NBUF == 2 ? ((t >> 1) & 1u) : (t & 1u); };
     uint32_t tcount = 0, s = (uint32_t)g, tpass = 0, rcount = 0;
     while (s >= nsub_out) {
       s -= nsub_out;
@@ -336,14 +353,14 @@ mtgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 
       // release the accumulators of the tiles this warp owns no block of
       for (; tpass < tcount; ++tpass) {
-        mbar_wait_parked(&acc_full[tpass & 1], (tpass >> 1) & 1);
+        mbar_wait_parked(&acc_full[acc_buf(tpass)], acc_par(tpass));
         if (lane == 0) {
-          if (PAIR) mbar_arrive_leader(&acc_empty[tpass & 1]);
-          else mbar_arrive(&acc_empty[tpass & 1]);
+          if (PAIR) mbar_arrive_leader(&acc_empty[acc_buf(tpass)]);
+          else mbar_arrive(&acc_empty[acc_buf(tpass)]);
         }
       }
-      const uint32_t b = tcount & 1;
-      mbar_wait_parked(&acc_full[b], (tcount >> 1) & 1);
+      const uint32_t b = acc_buf(tcount);
+      mbar_wait_parked(&acc_full[b], acc_par(tcount));
       tc_fence_after();
       const uint32_t tlane = tmem_base + b * Cfg::ACC_STRIDE + ((uint32_t)(q * 32) << 16);
 
@@ -697,10 +714,10 @@ mtgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       }
     }
     for (; tpass < num_tiles; ++tpass) {
-      mbar_wait_parked(&acc_full[tpass & 1], (tpass >> 1) & 1);
+      mbar_wait_parked(&acc_full[acc_buf(tpass)], acc_par(tpass));
       if (lane == 0) {
-        if (PAIR) mbar_arrive_leader(&acc_empty[tpass & 1]);
-        else mbar_arrive(&acc_empty[tpass & 1]);
+        if (PAIR) mbar_arrive_leader(&acc_empty[acc_buf(tpass)]);
+        else mbar_arrive(&acc_empty[acc_buf(tpass)]);
       }
     }
     if (p.tma_epi && lane == 0) tma_store_wait_all();  // all bulk stores of this thread have landed
@@ -752,7 +769,7 @@ static int launch(const b200svd_gemm_params* p, const CUtensorMap& tmA, const Ge
   CUtensorMap tmB;
   uint64_t bd[3] = {p->k, p->n, p->taps};
   uint64_t bs[2] = {(uint64_t)p->k * 2, (uint64_t)p->k * 2 * p->n};
-  uint32_t bb[3] = {64, (uint32_t)Cfg::B_ROWS, 1};
+  uint32_t bb[3] = {64, (uint32_t)(Cfg::B_ROWS / Cfg::NMMA), 1};
   if (encode_tmap_bf16(&tmB, p->w_ptr, 3, bd, bs, bb)) return 1;
   GemmDev dd = d;
   dd.n_tiles = (p->n + BN - 1) / BN;
@@ -990,6 +1007,15 @@ extern "C" int b200svd_gemm(const b200svd_gemm_params* p, void* stream) {
   // mode 3: two pairs on adjacent N tiles share (multicast) their A tile when the N tile count is even
   const uint32_t n_tiles_all = (p->n + (uint32_t)bn - 1) / (uint32_t)bn;
   const bool quad = pair && pm == 3 && (n_tiles_all % 2) == 0;
+  // 320-wide pair tile (B200SVD_BN320=1; single-buffered accumulator): long main loops only
+  static int bn320 = -1;
+  if (bn320 < 0) {
+    const char* e = getenv("B200SVD_BN320");
+    bn320 = e ? atoi(e) : 0;
+  }
+  if (bn320 && p->bn == 0 && (bn == 160 || bn == 256) && p->n % 320 == 0 && m_tiles_all >= 2 && pm >= 1 &&
+      p->act == B200SVD_ACT_NONE && (uint64_t)p->taps * d.kblocks >= 15)
+    bn = 320;
   // lean epilogue for everything without an activation (B200SVD_LEAN_EPI=0 keeps the generic loop: A/B knob)
   static int lean_epi = -1;
   if (lean_epi < 0) {
@@ -1005,6 +1031,13 @@ extern "C" int b200svd_gemm(const b200svd_gemm_params* p, void* stream) {
     set_error("b200svd_gemm: gn_part needs the activation-free bf16 epilogue (n %% 16 == 0, n > 64), gn_slot_sample and "
               "an 8-byte aligned partial buffer with gn_ld >= n");
     return 1;
+  }
+  if (bn == 320) {
+    if (m_tiles_all < 2 || p->n % 320 != 0 || p->act == B200SVD_ACT_GEGLU) {
+      set_error("b200svd_gemm: the 320-wide tile is a 2-SM tile: needs >= 2 M tiles, n %% 320 == 0, no GEGLU");
+      return 1;
+    }
+    return lean ? launch<320, 2, 2>(p, tmA, d, st) : launch<320, 2, 0>(p, tmA, d, st);
   }
   if (lean) {
     switch (bn) {

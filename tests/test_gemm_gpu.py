@@ -68,6 +68,54 @@ def test_wide_tiles_epilogue(cuda_dev, M, K, N, bn):
     _check(out, ref, f"wide tile M{M} K{K} N{N} bn{bn}")
 
 
+@pytest.mark.parametrize("M,K,N,bn", [(1357, 1280, 1280, 256), (384, 640, 640, 160), (2000, 1280, 640, 320),
+                                      (128 * 149 * 2 + 5, 320, 320, 320), (5000, 1280, 1008, 256), (777, 640, 640, 128),
+                                      (3000, 960, 960, 320), (4096, 2560, 1280, 0), (640, 320, 960, 0)])
+@pytest.mark.parametrize("operands", ["all", "bias", "none", "res1"])
+def test_lean_epilogue(cuda_dev, M, K, N, bn, operands):
+    """Activation-free launches take the specialised packed-math epilogue (mtgemm EPI = 2): bias, per-frame vector,
+    s_acc and both residuals in every combination the network uses; 128/160/256-wide tiles and the 320-wide 2-SM tile
+    (two N = 160 MMAs per k step, single-buffered accumulator), ragged M / N edges, several tiles per CTA."""
+    from streamingt2v_b200 import ops, packing
+    rpf = 64
+    x = _rand((M, K), cuda_dev, seed=1)
+    w = _rand((N, K), cuda_dev, K ** -0.5, seed=2)
+    b = torch.randn(N, device=cuda_dev)
+    fvec = torch.randn((M + rpf - 1) // rpf, N, device=cuda_dev)
+    r1 = _rand((M, N), cuda_dev, seed=3)
+    r2 = _rand((M, N), cuda_dev, seed=4)
+    v = x.float() @ w.float().t()
+    wp = packing.pack_linear(w, cuda_dev)
+    if operands == "all":
+        out = ops.linear(x, wp, b, fvec=fvec, rows_per_frame=rpf, s_acc=0.5, res1=r1, s1=0.7, res2=r2, s2=-0.5, bn=bn)
+        ref = 0.5 * (v + b + fvec.repeat_interleave(rpf, 0)[:M]) + 0.7 * r1.float() - 0.5 * r2.float()
+    elif operands == "bias":
+        out = ops.linear(x, wp, b, bn=bn)
+        ref = v + b
+    elif operands == "res1":
+        out = ops.linear(x, wp, b, res1=r1, s1=1.0, bn=bn)
+        ref = v + b + r1.float()
+    else:
+        out = ops.linear(x, wp, None, bn=bn)
+        ref = v
+    torch.cuda.synchronize()
+    _check(out, ref, f"lean epilogue M{M} K{K} N{N} bn{bn} {operands}")
+
+
+@pytest.mark.parametrize("Nf,H,W,Cin,Cout", [(4, 24, 64, 320, 320), (3, 18, 32, 640, 640), (2, 36, 64, 960, 320)])
+def test_conv3x3_320_wide_tile(cuda_dev, monkeypatch, Nf, H, W, Cin, Cout):
+    """3x3 convolutions on the 320-wide 2-SM tile (forced), bias + residual, against F.conv2d."""
+    from streamingt2v_b200 import ops, packing
+    x = _rand((Nf, H, W, Cin), cuda_dev, seed=1)
+    wt = _rand((Cout, Cin, 3, 3), cuda_dev, (9 * Cin) ** -0.5, seed=2)
+    b = torch.randn(Cout, device=cuda_dev)
+    r1 = _rand((Nf * H * W, Cout), cuda_dev, seed=3)
+    out = ops.conv3x3(x, packing.pack_conv3x3(wt, cuda_dev), b, res1=r1, s1=1.0, bn=320)
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), b, padding=1).permute(0, 2, 3, 1).reshape(-1, Cout)
+    _check(out, ref + r1.float(), f"conv3x3 bn320 {Nf}x{H}x{W} {Cin}->{Cout}", rtol=2 ** -7, atol=3e-2)
+
+
 def test_linear_epilogue(cuda_dev):
     from streamingt2v_b200 import ops, packing
     M, K, N, rpf = 640, 320, 320, 64
