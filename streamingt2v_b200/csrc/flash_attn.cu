@@ -676,8 +676,8 @@ extern "C" int b200svd_flash_attn(const void* qkv, int64_t ldqkv, void* out, int
   uint64_t strides[2] = {(uint64_t)ldqkv * 2, (uint64_t)ldqkv * 2 * (uint64_t)s};
   uint32_t box[3] = {64, 128, 1};
   if (encode_tmap_bf16(&tm, qkv, 3, dims, strides, box)) return 1;
-  // exp2 split between MUFU and the FMA pipe: B200SVD_FA_POLY = 0..4 of every 8 score pairs; B200SVD_FA_V = 3 selects
-  // the round-1 two-pass softmax, 4 (default) the single-pass one (tuning knobs)
+  // exp2 split between MUFU and the FMA pipe: B200SVD_FA_POLY = 0..4 of every 8 score pairs; B200SVD_FA_V = 3 (default)
+  // selects the two-pass softmax, 4 the single-pass one, 5 the 16-softmax-warp kernel (tuning knobs)
   static int poly = -1, fast = 1, v5 = 0;
   if (poly < 0) {
     {
@@ -690,7 +690,7 @@ extern "C" int b200svd_flash_attn(const void* qkv, int64_t ldqkv, void* out, int
     poly = ev ? atoi(ev) : FA_POLY_DEFAULT;
     if (poly < 0 || poly > 4) poly = FA_POLY_DEFAULT;
     const char* fv = getenv("B200SVD_FA_V");
-    fast = (fv && atoi(fv) == 3) ? 0 : 1;
+    fast = (fv && atoi(fv) == 4) ? 1 : 0;   // default: the round-1 two-pass softmax (v4 / v5 are opt-in experiments)
     cudaError_t e = cudaSuccess;
     auto set = [&](auto kern) {
       if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_BYTES);
