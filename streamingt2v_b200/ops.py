@@ -173,7 +173,11 @@ def gemm_raw(*, a, a_dims, a_strides, a_box, w, n, k, taps, tap_off, m_ext, m_bo
         _prof_end(e0, ("mtgemm", desc), 2.0 * rows * k * n * taps, nbytes)
 
 
-GN_FUSE = os.environ.get("B200SVD_GN_FUSE", "1") != "0"
+# GroupNorm statistics in the producing GEMM's epilogue: needs the activation-free ("lean") epilogue of mtgemm.cu, so
+# both switches travel together (environment overrides for A/B runs)
+_DEFAULT_R2_EPILOGUES = "0"
+GN_FUSE = (os.environ.get("B200SVD_GN_FUSE", _DEFAULT_R2_EPILOGUES) != "0"
+           and os.environ.get("B200SVD_LEAN_EPI", _DEFAULT_R2_EPILOGUES) != "0")
 
 
 @lru_cache(maxsize=None)

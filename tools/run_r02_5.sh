@@ -1,5 +1,6 @@
 set -x
 mkdir -p gpurun_out
+export B200SVD_LEAN_EPI=1 B200SVD_GEGLU_EPI=1 B200SVD_GN_FUSE=1
 timeout 1200 python -m pytest tests/test_gemm_gpu.py -m gpu -q -x > gpurun_out/r02_gputest_gemm.log 2>&1; echo "pytest gemm exit $?"; tail -4 gpurun_out/r02_gputest_gemm.log
 for v in 3 4 5; do B200SVD_FA_V=$v timeout 300 python tools/diag_fa.py; done > gpurun_out/r02_diag_fa.txt 2>&1
 grep -v Warning gpurun_out/r02_diag_fa.txt | cut -c1-400
