@@ -43,6 +43,7 @@ constexpr int FA_SMEM_BYTES = 2 * FA_Q_BYTES + FA_KV_STAGES * 2 * FA_KV_TILE_BYT
 constexpr int FA_TMEM_COLS = 512;  // score buffers [0,128) [128,256) [256,384) (P aliases the first 64 columns), O_A [384,448) O_B [448,512)
 constexpr int FA_THREADS = 12 * 32;  // warpgroup 0: TMA, MMA (+2 idle warps); warpgroups 1, 2: softmax of tile A, B
 constexpr float FA_RESCALE_THRESHOLD = 8.0f;  // log2 units
+#define B200SVD_DEFAULT_FA_V 3
 constexpr int FA_POLY_DEFAULT = 0;  // measured (tools/bench_fa.py): every 1/8 moved to the FMA pipe costs ~5%: the softmax
                                     // warps are bound by their own dependent-latency chain, not by MUFU throughput
 
@@ -61,7 +62,13 @@ struct FaParams {
 // falls back to the two-pass path below (rescale O and l, recompute P against the raised max).  TMEM loads are
 // software pipelined (next 32 columns in flight while the current 32 are processed), the scale/subtract and the
 // row-sum use packed FFMA2/FADD2, the max uses FMNMX3: ~3 issue slots per score instead of ~4.6, no MUFU-idle max pass.
-template <int POLY, bool FAST>
+// PP (v6, "MUFU ping-pong"): the softmax warp of tile A and the softmax warp of tile B that share a scheduler fall into
+// lock-step (when both are in their exp phase each gets half the MUFU pipe, so they finish together and then both run
+// their MUFU-free phase — TMEM store, fences, barriers, next scores — with the pipe idle: 2048 + ~900 cycles per pair
+// of blocks, MUFU 70 % busy).  A token per scheduler (two 64-thread named barriers per TMEM lane quadrant, the
+// FlashAttention-3 warp-group ping-pong applied to the MUFU pipe) makes the exp phases ALTERNATE: a warp runs its exp
+// phase alone at the full MUFU rate while its partner does everything else.
+template <int POLY, bool FAST, bool PP>
 __global__ void __launch_bounds__(FA_THREADS, 1)
 flash_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const FaParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];  // SWIZZLE_128B tiles need 1024-byte alignment
@@ -179,10 +186,22 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const FaParams p) {
     const uint32_t tO = tmem_base + 384 + x * 64 + tl;
     float m_used = -INFINITY, l_run = 0.f;
     const float c = p.scale_log2;
+    // MUFU token of this scheduler: tile A's warp waits on barrier 1+qd, tile B's on 5+qd; each arrives on the other's
+    const int tok_self = 1 + 4 * x + qd, tok_other = 1 + 4 * (x ^ 1) + qd;
+    if (PP && x == 1) named_bar_arrive(tok_other, 64);  // tile A goes first
 
     for (int j = 0; j < nkb; ++j) {
       const int k = 2 * j + x, bf = k % 3;
       const uint32_t tS = tmem_base + bf * 128 + tl;
+      bool tok_done = false;  // this block's exp phase has already held (and passed on) the token
+      auto tok_acquire = [&]() {
+        if (PP) named_bar_sync(tok_self, 64);
+      };
+      auto tok_release = [&]() {
+        // tile B does not hand the token back after its last block (nobody would take it)
+        if (PP && !(x == 1 && j == nkb - 1)) named_bar_arrive(tok_other, 64);
+        tok_done = true;
+      };
       mbar_wait(&s_full[bf], (k / 3) & 1);
       tc_fence_after();
       const int kbase = j * FA_BK;
@@ -215,18 +234,37 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const FaParams p) {
             pkf[pbase + i] = pack_bf16x2(a, b);
           }
         };
-        tmem_ld32(tS, sva);
-        tmem_ld_wait32(sva);
-        tmem_ld32(tS + 32, svb);
-        process(sva, 0);
-        tmem_ld_wait32(svb);
-        tmem_ld32(tS + 64, sva);
-        process(svb, 16);
-        tmem_ld_wait32(sva);
-        tmem_ld32(tS + 96, svb);
-        process(sva, 32);
-        tmem_ld_wait32(svb);
-        process(svb, 48);
+        if (PP) {
+          // loads and waits adjacent (the partner warp covers the TMEM latency); first scores are fetched BEFORE the
+          // token is taken
+          tmem_ld32(tS, sva);
+          tmem_ld_wait32(sva);
+          tok_acquire();
+          process(sva, 0);
+          tmem_ld32(tS + 32, svb);
+          tmem_ld_wait32(svb);
+          process(svb, 16);
+          tmem_ld32(tS + 64, sva);
+          tmem_ld_wait32(sva);
+          process(sva, 32);
+          tmem_ld32(tS + 96, svb);
+          tmem_ld_wait32(svb);
+          process(svb, 48);
+          tok_release();
+        } else {
+          tmem_ld32(tS, sva);
+          tmem_ld_wait32(sva);
+          tmem_ld32(tS + 32, svb);
+          process(sva, 0);
+          tmem_ld_wait32(svb);
+          tmem_ld32(tS + 64, sva);
+          process(svb, 16);
+          tmem_ld_wait32(sva);
+          tmem_ld32(tS + 96, svb);
+          process(sva, 32);
+          tmem_ld_wait32(svb);
+          process(svb, 48);
+        }
         const float mxf = fmaxf(mxa, mxb);
         const bool needf = (mxf - m_used) * c > FA_RESCALE_THRESHOLD;
         if (!__any_sync(0xffffffffu, needf)) {
@@ -303,6 +341,8 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const FaParams p) {
       // pass 2: P = exp2(S*c - m*c), packed bf16x2, written back over the S columns (first 64 of the tile's 128).
       // All 128 scores are read before any P column is written (P aliases S).
       uint32_t pk[64];
+      const bool take_tok = PP && !tok_done;  // a redone block already used its turn in the optimistic pass
+      if (take_tok) tok_acquire();
 #pragma unroll
       for (int c0 = 0; c0 < FA_BK; c0 += 32) {
         uint32_t sv[32];
@@ -329,6 +369,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const FaParams p) {
           pk[(c0 >> 1) + i] = pack_bf16x2(a, b);
         }
       }
+      if (take_tok) tok_release();
       {
         uint32_t t0[32], t1[32];
 #pragma unroll
@@ -678,31 +719,32 @@ extern "C" int b200svd_flash_attn(const void* qkv, int64_t ldqkv, void* out, int
   if (encode_tmap_bf16(&tm, qkv, 3, dims, strides, box)) return 1;
   // exp2 split between MUFU and the FMA pipe: B200SVD_FA_POLY = 0..4 of every 8 score pairs; B200SVD_FA_V = 3 (default)
   // selects the two-pass softmax, 4 the single-pass one, 5 the 16-softmax-warp kernel (tuning knobs)
-  static int poly = -1, fast = 1, v5 = 0;
+  static int poly = -1, fast = 0, v5 = 0, pp = 0;
   if (poly < 0) {
-    {
-      const char* fv5 = getenv("B200SVD_FA_V");
-      v5 = (fv5 && atoi(fv5) == 5) ? 1 : 0;
-      cudaError_t e5 = cudaFuncSetAttribute(flash_attn5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA5_SMEM_BYTES);
-      if (e5 != cudaSuccess) return cuda_fail(e5, "cudaFuncSetAttribute(flash_attn5)");
-    }
+    // B200SVD_FA_V: 3 (default) two-pass softmax, 4 single-pass, 5 sixteen softmax warps, 6 = two-pass + MUFU ping-pong,
+    // 7 = single-pass + MUFU ping-pong; B200SVD_FA_POLY = 0..2 of every 8 score pairs take exp2 on the FMA pipe
+    const char* fv = getenv("B200SVD_FA_V");
+    const int ver = fv ? atoi(fv) : B200SVD_DEFAULT_FA_V;
+    v5 = ver == 5;
+    fast = (ver == 4 || ver == 7) ? 1 : 0;
+    pp = (ver == 6 || ver == 7) ? 1 : 0;
     const char* ev = getenv("B200SVD_FA_POLY");
     poly = ev ? atoi(ev) : FA_POLY_DEFAULT;
-    if (poly < 0 || poly > 4) poly = FA_POLY_DEFAULT;
-    const char* fv = getenv("B200SVD_FA_V");
-    fast = (fv && atoi(fv) == 4) ? 1 : 0;   // default: the round-1 two-pass softmax (v4 / v5 are opt-in experiments)
-    cudaError_t e = cudaSuccess;
+    if (poly < 0 || poly > 2) poly = FA_POLY_DEFAULT;
+    cudaError_t e = cudaFuncSetAttribute(flash_attn5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA5_SMEM_BYTES);
     auto set = [&](auto kern) {
       if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_BYTES);
     };
-    set(flash_attn_kernel<0, false>);
-    set(flash_attn_kernel<1, false>);
-    set(flash_attn_kernel<2, false>);
-    set(flash_attn_kernel<0, true>);
-    set(flash_attn_kernel<1, true>);
-    set(flash_attn_kernel<2, true>);
-    set(flash_attn_kernel<3, true>);
-    set(flash_attn_kernel<4, true>);
+    set(flash_attn_kernel<0, false, false>);
+    set(flash_attn_kernel<1, false, false>);
+    set(flash_attn_kernel<2, false, false>);
+    set(flash_attn_kernel<0, true, false>);
+    set(flash_attn_kernel<1, true, false>);
+    set(flash_attn_kernel<2, true, false>);
+    set(flash_attn_kernel<0, false, true>);
+    set(flash_attn_kernel<0, true, true>);
+    set(flash_attn_kernel<1, true, true>);
+    set(flash_attn_kernel<2, true, true>);
     if (e != cudaSuccess) {
       poly = -1;
       return cuda_fail(e, "cudaFuncSetAttribute(flash_attn)");
@@ -717,23 +759,25 @@ extern "C" int b200svd_flash_attn(const void* qkv, int64_t ldqkv, void* out, int
   p.scale_log2 = scale * 1.4426950408889634f;
   dim3 grid((s + 2 * FA_BQ - 1) / (2 * FA_BQ), heads, n);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+#define FA_LAUNCH(P_, F_, PP_) flash_attn_kernel<P_, F_, PP_><<<grid, FA_THREADS, FA_SMEM_BYTES, st>>>(tm, p)
   if (v5) {
     flash_attn5_kernel<<<grid, FA5_THREADS, FA5_SMEM_BYTES, st>>>(tm, p);
+  } else if (fast && pp) {
+    if (poly == 0) FA_LAUNCH(0, true, true);
+    else if (poly == 1) FA_LAUNCH(1, true, true);
+    else FA_LAUNCH(2, true, true);
   } else if (fast) {
-    switch (poly) {
-      case 0: flash_attn_kernel<0, true><<<grid, FA_THREADS, FA_SMEM_BYTES, st>>>(tm, p); break;
-      case 1: flash_attn_kernel<1, true><<<grid, FA_THREADS, FA_SMEM_BYTES, st>>>(tm, p); break;
-      case 2: flash_attn_kernel<2, true><<<grid, FA_THREADS, FA_SMEM_BYTES, st>>>(tm, p); break;
-      case 3: flash_attn_kernel<3, true><<<grid, FA_THREADS, FA_SMEM_BYTES, st>>>(tm, p); break;
-      default: flash_attn_kernel<4, true><<<grid, FA_THREADS, FA_SMEM_BYTES, st>>>(tm, p); break;
-    }
+    if (poly == 0) FA_LAUNCH(0, true, false);
+    else if (poly == 1) FA_LAUNCH(1, true, false);
+    else FA_LAUNCH(2, true, false);
+  } else if (pp) {
+    FA_LAUNCH(0, false, true);
   } else {
-    switch (poly) {
-      case 0: flash_attn_kernel<0, false><<<grid, FA_THREADS, FA_SMEM_BYTES, st>>>(tm, p); break;
-      case 1: flash_attn_kernel<1, false><<<grid, FA_THREADS, FA_SMEM_BYTES, st>>>(tm, p); break;
-      default: flash_attn_kernel<2, false><<<grid, FA_THREADS, FA_SMEM_BYTES, st>>>(tm, p); break;
-    }
+    if (poly == 0) FA_LAUNCH(0, false, false);
+    else if (poly == 1) FA_LAUNCH(1, false, false);
+    else FA_LAUNCH(2, false, false);
   }
+#undef FA_LAUNCH
   B200_CHECK_LAUNCH("flash_attn");
   return 0;
 }
