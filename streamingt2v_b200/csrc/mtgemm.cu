@@ -694,25 +694,31 @@ mtgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           }
         }
       }
-      // this block's TMEM reads are done: hand the accumulator back, then store
+      // this block's TMEM reads are done; the accumulator is handed back when the warp LEAVES the tile (with more than
+      // four 64-column sub-blocks per tile — the 320-wide tile — a warp owns two blocks of the same tile, and a second
+      // arrival for one tile would complete the barrier phase early)
       tc_fence_before();
       __syncwarp();
+      const uint32_t s_cur = s;
+      const uint32_t tprev = tcount;
+      s += 4;
+      while (s >= nsub_out) {
+        s -= nsub_out;
+        ++tcount;
+      }
       if (lane == 0) {
-        if (PAIR) mbar_arrive_leader(&acc_empty[b]);
-        else mbar_arrive(&acc_empty[b]);
+        if (tcount != tprev) {
+          if (PAIR) mbar_arrive_leader(&acc_empty[b]);
+          else mbar_arrive(&acc_empty[b]);
+        }
         if (!skip && p.tma_epi) {
           tma_store_5d(subw == 64 ? &tmO64 : &tmO32, ob, (int)ocol0, (int)(mb1 + qo1), (int)(mb2 + qo2),
                        (int)(mb3 + qo3), 0);
           tma_store_commit();
         }
       }
-      tpass = tcount + 1;
-      s += 4;
-      const uint32_t tprev = tcount;
-      while (s >= nsub_out) {
-        s -= nsub_out;
-        ++tcount;
-      }
+      (void)s_cur;
+      tpass = (tcount != tprev) ? tprev + 1 : tprev;
       if (tcount < num_tiles) {
         if (tcount != tprev) decode_tile(p, tile_begin + tcount, PAIR ? 2u : 1u, rank, QUAD ? 2u : 1u, npair, n_tile, mb1, mb2, mb3);
         prefetch_residual();
@@ -1018,8 +1024,11 @@ extern "C" int b200svd_gemm(const b200svd_gemm_params* p, void* stream) {
     const char* e = getenv("B200SVD_BN320");
     bn320 = e ? atoi(e) : 0;
   }
-  if (bn320 && p->bn == 0 && (bn == 160 || bn == 256) && p->n % 320 == 0 && m_tiles_all >= 2 && pm >= 1 &&
-      p->act == B200SVD_ACT_NONE && (uint64_t)p->taps * d.kblocks >= 15)
+  // measured (profiles/r02_bench_vs_libs*.txt): wins for N = 320 (convs 0.69 -> 0.57 ms, 1.96 -> 1.58 ms; FF2 0.39 -> 0.355)
+  // and for the N = 640 linears (0.353 -> 0.317); loses on the N = 640 / 1280 convolutions, whose 256-wide tiles are
+  // double-buffered
+  if (bn320 && p->bn == 0 && (bn == 160 || bn == 256) && (p->n == 320 || (p->n == 640 && p->taps == 1)) &&
+      m_tiles_all >= 2 && pm >= 1 && p->act == B200SVD_ACT_NONE && (uint64_t)p->taps * d.kblocks >= 15)
     bn = 320;
   // lean epilogue for everything without an activation (B200SVD_LEAN_EPI=0 keeps the generic loop: A/B knob)
   static int lean_epi = -1;
