@@ -33,10 +33,11 @@
 #include "common.h"
 #include "ptx.cuh"
 
-// Defaults of the round-2 epilogue specialisations (each also has an environment switch for A/B runs).  They are turned
-// on here only after the GPU parity suite has passed with them.
-#define B200SVD_DEFAULT_LEAN_EPI 0
-#define B200SVD_DEFAULT_GEGLU_EPI 0
+// Defaults of the round-2 epilogue specialisations (each also has an environment switch for A/B runs).  On since the GPU
+// parity suite passed with them (tests/test_gemm_gpu.py: 216 cases; denoiser / chain / VAE goldens:
+// profiles/r02_gputest_parity_newepi.log).
+#define B200SVD_DEFAULT_LEAN_EPI 1
+#define B200SVD_DEFAULT_GEGLU_EPI 1
 
 namespace b200 {
 
@@ -1027,8 +1028,11 @@ extern "C" int b200svd_gemm(const b200svd_gemm_params* p, void* stream) {
   // measured (profiles/r02_bench_vs_libs*.txt): wins for N = 320 (convs 0.69 -> 0.57 ms, 1.96 -> 1.58 ms; FF2 0.39 -> 0.355)
   // and for the N = 640 linears (0.353 -> 0.317); loses on the N = 640 / 1280 convolutions, whose 256-wide tiles are
   // double-buffered
-  if (bn320 && p->bn == 0 && (bn == 160 || bn == 256) && (p->n == 320 || (p->n == 640 && p->taps == 1)) &&
-      m_tiles_all >= 2 && pm >= 1 && p->act == B200SVD_ACT_NONE && (uint64_t)p->taps * d.kblocks >= 15)
+  // mode 2 additionally takes the N = 640 convolutions (the 256-wide tile computes 768 columns for them: 17 % of the
+  // tensor work is spent on zero-filled weight rows)
+  if (bn320 && p->bn == 0 && (bn == 160 || bn == 256) &&
+      (p->n == 320 || (p->n == 640 && (p->taps == 1 || bn320 >= 2))) && m_tiles_all >= 2 && pm >= 1 &&
+      p->act == B200SVD_ACT_NONE && (uint64_t)p->taps * d.kblocks >= 15)
     bn = 320;
   // lean epilogue for everything without an activation (B200SVD_LEAN_EPI=0 keeps the generic loop: A/B knob)
   static int lean_epi = -1;

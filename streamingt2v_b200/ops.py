@@ -175,9 +175,9 @@ def gemm_raw(*, a, a_dims, a_strides, a_box, w, n, k, taps, tap_off, m_ext, m_bo
 
 # GroupNorm statistics in the producing GEMM's epilogue: needs the activation-free ("lean") epilogue of mtgemm.cu, so
 # both switches travel together (environment overrides for A/B runs)
-_DEFAULT_R2_EPILOGUES = "0"
-GN_FUSE = (os.environ.get("B200SVD_GN_FUSE", _DEFAULT_R2_EPILOGUES) != "0"
-           and os.environ.get("B200SVD_LEAN_EPI", _DEFAULT_R2_EPILOGUES) != "0")
+# Off by default: measured neutral inside the step (groupnorm -0.5 ms, GEMM epilogues +3 ms on a power-capped B200,
+# profiles/r02_bench_newepi_gnfuse.json vs r02_bench_newepi.json); B200SVD_GN_FUSE=1 turns it on.
+GN_FUSE = (os.environ.get("B200SVD_GN_FUSE", "0") != "0" and os.environ.get("B200SVD_LEAN_EPI", "1") != "0")
 
 
 @lru_cache(maxsize=None)
