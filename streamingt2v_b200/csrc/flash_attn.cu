@@ -43,7 +43,7 @@ constexpr int FA_SMEM_BYTES = 2 * FA_Q_BYTES + FA_KV_STAGES * 2 * FA_KV_TILE_BYT
 constexpr int FA_TMEM_COLS = 512;  // score buffers [0,128) [128,256) [256,384) (P aliases the first 64 columns), O_A [384,448) O_B [448,512)
 constexpr int FA_THREADS = 12 * 32;  // warpgroup 0: TMA, MMA (+2 idle warps); warpgroups 1, 2: softmax of tile A, B
 constexpr float FA_RESCALE_THRESHOLD = 8.0f;  // log2 units
-#define B200SVD_DEFAULT_FA_V 3
+#define B200SVD_DEFAULT_FA_V 4
 constexpr int FA_POLY_DEFAULT = 0;  // measured (tools/bench_fa.py): every 1/8 moved to the FMA pipe costs ~5%: the softmax
                                     // warps are bound by their own dependent-latency chain, not by MUFU throughput
 
