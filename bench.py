@@ -496,7 +496,10 @@ def run_ours(args):
                 "share_of_step": g["ms"] / sum(v["ms"] for v in prof.families.values()),
                 "traffic": None, "traffic_note": "see profiles/ for the ncu --set full capture of this kernel"}
         try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))["mtgemm_conv3x3_L0_320to320"]
+            tpath = os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")
+            if not os.path.exists(tpath):
+                tpath = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+            tr = json.load(open(tpath))["mtgemm_conv3x3_L0_320to320"]
             roof["traffic"] = tr["traffic_bytes"]
             roof["traffic_note"] = (f"ncu --set full, one launch of the dominant conv shape ({tr['launch']}): "
                                     f"{tr['traffic_bytes'] / 1e6:.0f} MB DRAM vs {tr['algorithmic_bytes'] / 1e6:.0f} MB "
