@@ -470,9 +470,10 @@ def run_ours(args):
     # ---------------- per-family live profile (one extra step, outside the timed regions) ----------------
     roof = None
     fam = None
+    # every rank takes the step (in pair mode it contains the pair's all-gather); rank 0 reports
+    with ops.profile() as prof:
+        step(cur, td, cd, ctrl_d, 1)
     if rank == 0:
-        with ops.profile() as prof:
-            step(cur, td, cd, ctrl_d, 1)
         fam = {k: dict(launches=v["launches"], ms=round(v["ms"], 3), tflops=round(v["flops"] / 1e12, 3),
                        gbytes=round(v["bytes"] / 1e9, 3)) for k, v in prof.families.items()}
         if os.environ.get("B200SVD_BENCH_SHAPES"):

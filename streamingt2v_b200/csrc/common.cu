@@ -129,8 +129,7 @@ int b200svd_init(int device) {
                     device, prop.major, prop.minor);
     return 1;
   }
-  e = cudaSetDevice(device);
-  if (e != cudaSuccess) return b200::cuda_fail(e, "cudaSetDevice");
+  // no cudaSetDevice here: the caller (PyTorch) owns the current device; launches go to the caller's stream
   return b200::resolve_encode();
 }
 

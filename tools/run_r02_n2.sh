@@ -1,8 +1,6 @@
 set -x
 mkdir -p gpurun_out
 nvidia-smi -L
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/r02_bench_n2_latency.json 2> gpurun_out/r02_bench_n2_latency.err; echo "n2 latency exit $?"
-tail -c 2500 gpurun_out/r02_bench_n2_latency.json
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 10 --warmup 3 --mode throughput > gpurun_out/r02_bench_n2_throughput.json 2> gpurun_out/r02_bench_n2_throughput.err; echo "n2 throughput exit $?"
-tail -c 800 gpurun_out/r02_bench_n2_throughput.json
-tail -5 gpurun_out/r02_bench_n2_latency.err
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/r02_bench_n2_latency.json 2> gpurun_out/r02_bench_n2_latency.err; echo "n2 latency exit $?"
+tail -c 1200 gpurun_out/r02_bench_n2_latency.json
+tail -3 gpurun_out/r02_bench_n2_latency.err
