@@ -389,6 +389,293 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const FaParams p) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// v5: SIXTEEN softmax warps.  The v3/v4 kernel is latency bound: with two softmax warps per scheduler neither the
+// MUFU pipe (70 % busy), nor the issue slots (47 %), nor the tensor pipe (31 %) saturate, fewer instructions (v4) or
+// fewer MUFU operations (exp2 on the FMA pipe) do not help.  v5 splits every query row over TWO threads (key columns
+// [0,64) and [64,128) of each block, warps w and w+4 share a TMEM lane quadrant), so that four softmax warps per
+// scheduler hide each other's TMEM / MUFU / barrier latencies.  The two halves of a row keep the same running max:
+// they exchange their block maxima through shared memory (one 64-thread named barrier per block), take the same
+// decision (commit the optimistic probabilities or redo against a raised max), keep partial row sums and rescale /
+// normalise disjoint halves of the O columns.  P of half h lives in the first 32 columns of that half's own score
+// columns (no aliasing between the halves), so the PV MMAs read their A operand from two places.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int FA5_THREADS = 20 * 32;
+constexpr int FA5_XCH_BYTES = 2 * 2 * 4 * 2 * 32 * 4;  // [parity][tile][quadrant][half][lane] floats
+constexpr int FA5_SMEM_BYTES = FA_SMEM_BYTES + FA5_XCH_BYTES;
+
+__global__ void __launch_bounds__(FA5_THREADS, 1)
+flash_attn5_kernel(const __grid_constant__ CUtensorMap tmQKV, const FaParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  uint8_t* sQ = smem;
+  uint8_t* sKV = sQ + 2 * FA_Q_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + FA_KV_STAGES * 2 * FA_KV_TILE_BYTES);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;
+  uint64_t* kv_empty = kv_full + FA_KV_STAGES;
+  uint64_t* s_full = kv_empty + FA_KV_STAGES;
+  uint64_t* p_full = s_full + 3;
+  uint64_t* pv_done = p_full + 3;
+  uint64_t* o_done = pv_done + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
+  float* xch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int head = blockIdx.y, n = blockIdx.z;
+  const int q0 = blockIdx.x * (2 * FA_BQ);
+  const int nkb = (p.S + FA_BK - 1) / FA_BK;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmQKV);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < FA_KV_STAGES; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+    }
+    for (int bf = 0; bf < 3; ++bf) {
+      mbar_init(&s_full[bf], 1);
+      mbar_init(&p_full[bf], 8);  // one arrive per softmax warp of the tile (4 quadrants x 2 column halves)
+    }
+    for (int x = 0; x < 2; ++x) {
+      mbar_init(&pv_done[x], 1);
+      mbar_init(&o_done[x], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, FA_TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (warp == 0) {
+      if (lane == 0) {
+        // ===================== TMA producer =====================
+        mbar_expect_tx(q_full, 2 * FA_Q_BYTES);
+        tma_load_3d(sQ, &tmQKV, q_full, head * FA_D, q0, n);
+        tma_load_3d(sQ + FA_Q_BYTES, &tmQKV, q_full, head * FA_D, q0 + FA_BQ, n);
+        for (int j = 0; j < nkb; ++j) {
+          const int s = j % FA_KV_STAGES;
+          const uint32_t ph = (j / FA_KV_STAGES) & 1;
+          mbar_wait(&kv_empty[s], ph ^ 1);
+          uint8_t* sk = sKV + s * 2 * FA_KV_TILE_BYTES;
+          mbar_expect_tx(&kv_full[s], 2 * FA_KV_TILE_BYTES);
+          tma_load_3d(sk, &tmQKV, &kv_full[s], p.C + head * FA_D, j * FA_BK, n);
+          tma_load_3d(sk + FA_KV_TILE_BYTES, &tmQKV, &kv_full[s], 2 * p.C + head * FA_D, j * FA_BK, n);
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        // ===================== MMA issuer (as v3/v4; P is read from two 32-column pieces) =====================
+        constexpr uint32_t idesc_qk = make_idesc_f16(128, 128, 1, 0, 0);
+        constexpr uint32_t idesc_pv = make_idesc_f16(128, 64, 1, 0, 1);
+        const uint64_t qdesc[2] = {smem_desc_k_sw128(smem_u32(sQ)), smem_desc_k_sw128(smem_u32(sQ + FA_Q_BYTES))};
+        mbar_wait(q_full, 0);
+        const int nitems = 2 * nkb;
+        int kv_ready = -1;
+        auto issue_qk = [&](int k) {
+          const int j = k >> 1, x = k & 1, bf = k % 3;
+          if (j > kv_ready) {
+            mbar_wait(&kv_full[j % FA_KV_STAGES], (j / FA_KV_STAGES) & 1);
+            tc_fence_after();
+            kv_ready = j;
+          }
+          const uint64_t kdesc = smem_desc_k_sw128(smem_u32(sKV + (j % FA_KV_STAGES) * 2 * FA_KV_TILE_BYTES));
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            umma_f16_ss(tmem_base + bf * 128, qdesc[x] + kk * 2, kdesc + kk * 2, idesc_qk, kk > 0);
+          umma_commit(&s_full[bf]);
+        };
+        for (int k = 0; k < 3 && k < nitems; ++k) issue_qk(k);
+        for (int k = 0; k < nitems; ++k) {
+          const int j = k >> 1, x = k & 1, bf = k % 3;
+          const int st = j % FA_KV_STAGES;
+          mbar_wait(&p_full[bf], (k / 3) & 1);
+          tc_fence_after();
+          const uint64_t vdesc = smem_desc_mn_sw128(smem_u32(sKV + st * 2 * FA_KV_TILE_BYTES + FA_KV_TILE_BYTES));
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) {
+            // keys [16 kk, 16 kk + 16): 8 packed columns; half 0 at buffer columns [0,32), half 1 at [64,96)
+            const uint32_t pa = tmem_base + bf * 128 + (kk < 4 ? kk * 8 : 64 + (kk - 4) * 8);
+            umma_f16_ts(tmem_base + 384 + x * 64, pa, vdesc + (uint64_t)(kk * 128), idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
+          }
+          umma_commit(&pv_done[x]);
+          if (j == nkb - 1) umma_commit(&o_done[x]);
+          if (x == 1) umma_commit(&kv_empty[st]);
+          if (k + 3 < nitems) issue_qk(k + 3);
+        }
+      }
+      __syncwarp();
+    }
+  } else {
+    // the pool only holds what warpgroup 0 gave back: 128 x (96 - 40) = 7168 registers = 512 x 14 -> 104 per softmax thread
+    // (asking for 112 with 48 left in warpgroup 0 needed 8192 of 6144 and blocked forever: the first version hung)
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    // ===================== softmax warps 4..19: tile x, column half hf, TMEM lane quadrant qd =====================
+    const int e = warp - 4;
+    const int x = e >> 3;
+    const int hf = (e >> 2) & 1;
+    const int qd = warp & 3;
+    const int r = qd * 32 + lane;
+    const uint32_t tl = ((uint32_t)(qd * 32)) << 16;
+    const uint32_t tO = tmem_base + 384 + x * 64 + 32 * hf + tl;  // this thread's 32 O columns
+    const int bar_id = 1 + x * 4 + qd;
+    auto slot = [&](int par, int h) -> float* { return xch + ((((par * 2 + x) * 4 + qd) * 2 + h) * 32) + lane; };
+    float m_used = -INFINITY, l_run = 0.f;
+    const float c = p.scale_log2;
+
+    for (int j = 0; j < nkb; ++j) {
+      const int k = 2 * j + x, bf = k % 3;
+      const uint32_t tS = tmem_base + bf * 128 + 64 * hf + tl;  // my 64 score columns; P goes over the first 32
+      mbar_wait(&s_full[bf], (k / 3) & 1);
+      tc_fence_after();
+      const int kbase = j * FA_BK + 64 * hf;
+      const bool tail = j * FA_BK + FA_BK > p.S;
+      uint32_t pk[32];
+      float lsum = 0.f, rowmax;
+      bool committed = false;
+      if (j > 0 && !tail) {
+        // optimistic single pass against the running max; the block max is tracked on the side
+        const float mbf = m_used * c;
+        const f32x2 c2 = pack2(c, c), nmb2 = pack2(-mbf, -mbf);
+        f32x2 la = pack2(0.f, 0.f), lb = pack2(0.f, 0.f);
+        float mxa = -INFINITY, mxb = -INFINITY;
+#pragma unroll
+        for (int c0 = 0; c0 < 64; c0 += 32) {
+          uint32_t sv[32];
+          tmem_ld32(tS + c0, sv);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float s0 = __uint_as_float(sv[2 * i]), s1 = __uint_as_float(sv[2 * i + 1]);
+            if (i & 1) mxb = max3f(mxb, s0, s1);
+            else mxa = max3f(mxa, s0, s1);
+            float xa, xb;
+            unpack2(fma2(pack2(s0, s1), c2, nmb2), xa, xb);
+            const float a = ex2_approx(xa), b = ex2_approx(xb);
+            if (i & 1) lb = add2(lb, pack2(a, b));
+            else la = add2(la, pack2(a, b));
+            pk[(c0 >> 1) + i] = pack_bf16x2(a, b);
+          }
+        }
+        const float mx = fmaxf(mxa, mxb);
+        *slot(j & 1, hf) = mx;
+        named_bar_sync(bar_id, 64);
+        rowmax = fmaxf(mx, *slot(j & 1, hf ^ 1));
+        if (!__any_sync(0xffffffffu, (rowmax - m_used) * c > FA_RESCALE_THRESHOLD)) {
+          float l0, l1, l2, l3;
+          unpack2(la, l0, l1);
+          unpack2(lb, l2, l3);
+          lsum = (l0 + l1) + (l2 + l3);
+          committed = true;
+        }
+      } else {
+        // first block / ragged last block: the row max has to be known first
+        float mx = -INFINITY;
+#pragma unroll
+        for (int c0 = 0; c0 < 64; c0 += 32) {
+          uint32_t sv[32];
+          tmem_ld32(tS + c0, sv);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float sx = __uint_as_float(sv[i]);
+            if (tail && kbase + c0 + i >= p.S) sx = -INFINITY;
+            mx = fmaxf(mx, sx);
+          }
+        }
+        *slot(j & 1, hf) = mx;
+        named_bar_sync(bar_id, 64);
+        rowmax = fmaxf(mx, *slot(j & 1, hf ^ 1));
+      }
+      if (!committed) {
+        if (j == 0) {
+          m_used = rowmax;
+        } else {
+          const bool need = (rowmax - m_used) * c > FA_RESCALE_THRESHOLD;
+          if (__any_sync(0xffffffffu, need)) {
+            // raise the running max: rescale this thread's half of the O columns and its partial row sum
+            mbar_wait(&pv_done[x], (j - 1) & 1);
+            tc_fence_after();
+            const float m_new = need ? rowmax : m_used;
+            const float alpha = exp2f((m_used - m_new) * c);
+            uint32_t ov[32];
+            tmem_ld32(tO, ov);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
+            tmem_st32(tO, ov);
+            tmem_st_wait();
+            l_run *= alpha;
+            m_used = m_new;
+          }
+        }
+        const float mb = m_used * c;
+        float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+        for (int c0 = 0; c0 < 64; c0 += 32) {
+          uint32_t sv[32];
+          tmem_ld32(tS + c0, sv);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float a = ex2_approx(fmaf(__uint_as_float(sv[2 * i]), c, -mb));
+            float b = ex2_approx(fmaf(__uint_as_float(sv[2 * i + 1]), c, -mb));
+            if (tail) {
+              if (kbase + c0 + 2 * i >= p.S) a = 0.f;
+              if (kbase + c0 + 2 * i + 1 >= p.S) b = 0.f;
+            }
+            l0 += a;
+            l1 += b;
+            pk[(c0 >> 1) + i] = pack_bf16x2(a, b);
+          }
+        }
+        lsum = l0 + l1;
+      }
+      tmem_st32(tS, pk);
+      l_run += lsum;
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[bf]);
+    }
+    // epilogue: row sum = the two partial sums; this thread normalises and writes 32 of the 64 output columns
+    mbar_wait(&o_done[x], 0);   // completes once, after the tile's last PV (a parity wait on pv_done is ambiguous here)
+    tc_fence_after();
+    *slot(nkb & 1, hf) = l_run;
+    named_bar_sync(bar_id, 64);
+    const float inv = 1.0f / (l_run + *slot(nkb & 1, hf ^ 1));
+    const int qrow = q0 + x * FA_BQ + r;
+    uint32_t ov[32];
+    tmem_ld32(tO, ov);
+    tmem_ld_wait();
+    if (qrow < p.S) {
+      __nv_bfloat16* dst = p.out + ((int64_t)n * p.S + qrow) * p.ldo + head * FA_D + 32 * hf;
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        reinterpret_cast<uint4*>(dst)[cc] =
+            make_uint4(pack_bf16x2(__uint_as_float(ov[8 * cc]) * inv, __uint_as_float(ov[8 * cc + 1]) * inv),
+                       pack_bf16x2(__uint_as_float(ov[8 * cc + 2]) * inv, __uint_as_float(ov[8 * cc + 3]) * inv),
+                       pack_bf16x2(__uint_as_float(ov[8 * cc + 4]) * inv, __uint_as_float(ov[8 * cc + 5]) * inv),
+                       pack_bf16x2(__uint_as_float(ov[8 * cc + 6]) * inv, __uint_as_float(ov[8 * cc + 7]) * inv));
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, FA_TMEM_COLS);
+  }
+}
+
 }  // namespace b200
 
 // qkv: [(n s), ldqkv] bf16 with columns [q | k | v], each C = heads*64 wide; out: [(n s), ldo] bf16 (C columns).
@@ -407,17 +694,18 @@ extern "C" int b200svd_flash_attn(const void* qkv, int64_t ldqkv, void* out, int
   if (encode_tmap_bf16(&tm, qkv, 3, dims, strides, box)) return 1;
   // exp2 split between MUFU and the FMA pipe: B200SVD_FA_POLY = 0..4 of every 8 score pairs; B200SVD_FA_V = 3 (default)
   // selects the two-pass softmax, 4 the single-pass one, 5 the 16-softmax-warp kernel (tuning knobs)
-  static int poly = -1, fast = 0;
+  static int poly = -1, fast = 0, v5 = 0;
   if (poly < 0) {
     // B200SVD_FA_V: 3 = two-pass softmax, 4 = single optimistic pass (see the kernel comment); B200SVD_FA_POLY = 0..2 of
     // every 8 score pairs take their exp2 on the FMA pipe (measured slower, profiles/r02_bench_fa_*.txt)
     const char* fv = getenv("B200SVD_FA_V");
     const int ver = fv ? atoi(fv) : B200SVD_DEFAULT_FA_V;
     fast = ver == 4 ? 1 : 0;
+    v5 = ver == 5 ? 1 : 0;   // sixteen softmax warps (two threads per query row)
     const char* ev = getenv("B200SVD_FA_POLY");
     poly = ev ? atoi(ev) : FA_POLY_DEFAULT;
     if (poly < 0 || poly > 2) poly = FA_POLY_DEFAULT;
-    cudaError_t e = cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(flash_attn5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA5_SMEM_BYTES);
     auto set = [&](auto kern) {
       if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM_BYTES);
     };
@@ -442,7 +730,9 @@ extern "C" int b200svd_flash_attn(const void* qkv, int64_t ldqkv, void* out, int
   dim3 grid((s + 2 * FA_BQ - 1) / (2 * FA_BQ), heads, n);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
 #define FA_LAUNCH(P_, F_) flash_attn_kernel<P_, F_><<<grid, FA_THREADS, FA_SMEM_BYTES, st>>>(tm, p)
-  if (fast) {
+  if (v5) {
+    flash_attn5_kernel<<<grid, FA5_THREADS, FA5_SMEM_BYTES, st>>>(tm, p);
+  } else if (fast) {
     if (poly == 0) FA_LAUNCH(0, true);
     else if (poly == 1) FA_LAUNCH(1, true);
     else FA_LAUNCH(2, true);
