@@ -106,6 +106,11 @@ int b200svd_gemm_pair_mode(int mode);
 int b200svd_flash_attn(const void* qkv, int64_t ldqkv, void* out, int64_t ldo, int n, int s, int heads, float scale,
                        void* stream);
 
+/* Tuning knob (no reference counterpart): softmax organisation of b200svd_flash_attn.  3 = two passes over the scores
+ * (block max, then exp), 4 = one optimistic pass (default), 5 = sixteen softmax warps (each query row split over two
+ * threads).  All three are parity-tested; other values only query.  Returns the previous variant. */
+int b200svd_flash_attn_variant(int v);
+
 /* ---- small-sequence attention, head dim 64, one warp per (batch, pixel, head) -----------------------------
  * Temporal self-attention (video_attention.py:145-148), CAM cross-frame attention (cam/conditioning.py:65-68),
  * temporal cross-attention over APM tokens (video_attention.py:150-154).  Row addressing:

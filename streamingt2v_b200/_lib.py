@@ -82,6 +82,8 @@ def load():
     _declare(lib)
     lib.b200svd_gemm_pair_mode.restype = C.c_int
     lib.b200svd_gemm_pair_mode.argtypes = [C.c_int]
+    lib.b200svd_flash_attn_variant.restype = C.c_int
+    lib.b200svd_flash_attn_variant.argtypes = [C.c_int]
     lib.b200svd_gn_scratch_doubles.restype = C.c_int64
     lib.b200svd_gn_scratch_doubles.argtypes = [C.c_int64, C.c_int64, C.c_int]
     _LIB = lib

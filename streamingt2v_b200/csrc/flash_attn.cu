@@ -676,7 +676,23 @@ flash_attn5_kernel(const __grid_constant__ CUtensorMap tmQKV, const FaParams p) 
   }
 }
 
+static int g_fa_variant = -1;  // 3 two-pass softmax, 4 single optimistic pass (default), 5 sixteen softmax warps
+static int fa_variant() {
+  if (g_fa_variant < 0) {
+    const char* fv = getenv("B200SVD_FA_V");
+    g_fa_variant = fv ? atoi(fv) : B200SVD_DEFAULT_FA_V;
+    if (g_fa_variant < 3 || g_fa_variant > 5) g_fa_variant = B200SVD_DEFAULT_FA_V;
+  }
+  return g_fa_variant;
+}
+
 }  // namespace b200
+
+extern "C" int b200svd_flash_attn_variant(int v) {
+  const int prev = b200::fa_variant();
+  if (v >= 3 && v <= 5) b200::g_fa_variant = v;
+  return prev;
+}
 
 // qkv: [(n s), ldqkv] bf16 with columns [q | k | v], each C = heads*64 wide; out: [(n s), ldo] bf16 (C columns).
 extern "C" int b200svd_flash_attn(const void* qkv, int64_t ldqkv, void* out, int64_t ldo, int n, int s, int heads,
@@ -692,16 +708,13 @@ extern "C" int b200svd_flash_attn(const void* qkv, int64_t ldqkv, void* out, int
   uint64_t strides[2] = {(uint64_t)ldqkv * 2, (uint64_t)ldqkv * 2 * (uint64_t)s};
   uint32_t box[3] = {64, 128, 1};
   if (encode_tmap_bf16(&tm, qkv, 3, dims, strides, box)) return 1;
-  // exp2 split between MUFU and the FMA pipe: B200SVD_FA_POLY = 0..4 of every 8 score pairs; B200SVD_FA_V = 3 (default)
-  // selects the two-pass softmax, 4 the single-pass one, 5 the 16-softmax-warp kernel (tuning knobs)
-  static int poly = -1, fast = 0, v5 = 0;
+  // B200SVD_FA_V / b200svd_flash_attn_variant: 3 = two-pass softmax, 4 = single optimistic pass (default), 5 = sixteen
+  // softmax warps; B200SVD_FA_POLY = 0..2 of every 8 score pairs take their exp2 on the FMA pipe (measured slower,
+  // profiles/r02_bench_fa_*.txt)
+  static int poly = -1;
+  const int ver = fa_variant();
+  const int fast = ver == 4 ? 1 : 0, v5 = ver == 5 ? 1 : 0;
   if (poly < 0) {
-    // B200SVD_FA_V: 3 = two-pass softmax, 4 = single optimistic pass (see the kernel comment); B200SVD_FA_POLY = 0..2 of
-    // every 8 score pairs take their exp2 on the FMA pipe (measured slower, profiles/r02_bench_fa_*.txt)
-    const char* fv = getenv("B200SVD_FA_V");
-    const int ver = fv ? atoi(fv) : B200SVD_DEFAULT_FA_V;
-    fast = ver == 4 ? 1 : 0;
-    v5 = ver == 5 ? 1 : 0;   // sixteen softmax warps (two threads per query row)
     const char* ev = getenv("B200SVD_FA_POLY");
     poly = ev ? atoi(ev) : FA_POLY_DEFAULT;
     if (poly < 0 || poly > 2) poly = FA_POLY_DEFAULT;

@@ -30,6 +30,12 @@ def gemm_pair_mode(mode: int = -1) -> int:
     return int(_lib.load().b200svd_gemm_pair_mode(int(mode)))
 
 
+def flash_attn_variant(v: int = -1) -> int:
+    """Softmax organisation of flash_attn: 3 two-pass, 4 single optimistic pass (default), 5 sixteen softmax warps.
+    Any other value only queries.  Returns the previous variant."""
+    return int(_lib.load().b200svd_flash_attn_variant(int(v)))
+
+
 class profile:
     """Context manager: brackets every launch with CUDA events on the launching stream and returns per-family
     (launches, total ms, algorithmic FLOPs, algorithmic bytes).  Used by bench.py for the live roofline numbers;

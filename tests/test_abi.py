@@ -23,7 +23,7 @@ def test_exports_match_header():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in b200svd.h but not exported"
     table = set(_lib.PROTOTYPES) | {"b200svd_last_error", "b200svd_version", "b200svd_init",
-                                    "b200svd_gn_scratch_doubles", "b200svd_gemm_pair_mode"}
+                                    "b200svd_gn_scratch_doubles", "b200svd_gemm_pair_mode", "b200svd_flash_attn_variant"}
     assert table == set(names), (sorted(table - set(names)), sorted(set(names) - table))
     assert lib.b200svd_version() >= 100
 

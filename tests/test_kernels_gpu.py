@@ -25,9 +25,18 @@ def _rand(shape, dev, scale=1.0, seed=0):
     return (torch.randn(shape, generator=g) * scale).to(dev).to(torch.bfloat16)
 
 
+@pytest.fixture(params=[3, 4, 5], ids=["two-pass", "single-pass", "16-warp"])
+def fa_variant(request, cuda_dev):
+    """Every FlashAttention case runs with each softmax organisation of the kernel (b200svd_flash_attn_variant)."""
+    from streamingt2v_b200 import ops
+    prev = ops.flash_attn_variant(request.param)
+    yield request.param
+    ops.flash_attn_variant(prev)
+
+
 @pytest.mark.parametrize("n,s,heads", [(2, 256, 5), (3, 144, 2), (1, 576, 20), (2, 4, 10), (1, 1000, 5), (2, 2304, 10),
                                        (1, 9216, 5), (4, 64, 5), (3, 129, 1)])
-def test_flash_attn(cuda_dev, n, s, heads):
+def test_flash_attn(cuda_dev, fa_variant, n, s, heads):
     from streamingt2v_b200 import ops
     Cc = heads * 64
     qkv = _rand((n * s, 3 * Cc), cuda_dev, 1.5, seed=n * 1000 + s)
@@ -39,7 +48,7 @@ def test_flash_attn(cuda_dev, n, s, heads):
 
 
 @pytest.mark.parametrize("s,ramp", [(1024, 6.0), (2304, 3.0), (640, 12.0)])
-def test_flash_attn_rising_max(cuda_dev, s, ramp):
+def test_flash_attn_rising_max(cuda_dev, fa_variant, s, ramp):
     """Key magnitudes grow along the sequence, so the row maxima keep rising by more than 2^8 between key blocks: the
     single-pass softmax must take its redo path (rescale O and l, recompute P) and still match SDPA."""
     from streamingt2v_b200 import ops
