@@ -185,6 +185,11 @@ def cpu_reference_sample(runs=1, warmup=0, budget_s=200.0, big_sample_budget_s=1
     cores = _usable_cores()
     torch.set_num_threads(cores)
     cfg = arch.UNetConfig()
+    if os.environ.get("B200SVD_BENCH_CONTRACT_TEST"):
+        # tests/test_bench_contract.py only: exercise the arm's plumbing on the reduced-width network in seconds; the
+        # printed sample says so and such a line is never a measurement
+        cfg = arch.TINY
+        big_sample_budget_s = 0.0
     sd_u, sd_c = _oracle_weights(cfg)
     full_flops = oracle_flops(cfg, 25, 72, 128)
 
@@ -216,7 +221,8 @@ def cpu_reference_sample(runs=1, warmup=0, budget_s=200.0, big_sample_budget_s=1
         dt, n = (timed(T, h, w, runs, warmup, budget_s) if runs > 1 else (probe_dt, probe_n))
     ratio = full_flops / f_s
     return dict(value=1.0 / (dt * ratio), unit=UNIT, cores=cores, kind="port",
-                sample=f"oracle port (fp32 torch-CPU, {cores} threads) of StreamingWrapper.forward, full-size weights, "
+                sample=("[CONTRACT TEST, reduced-width network — not a measurement] " if cfg is arch.TINY else "") +
+                       f"oracle port (fp32 torch-CPU, {cores} threads) of StreamingWrapper.forward, full-size weights, "
                        f"B=2 T={T} latent {h}x{w} ({f_s / 1e12:.2f} TFLOP): {dt:.2f}s/forward over {n} run(s) "
                        f"= {f_s / dt / 1e12:.2f} TFLOP/s; scaled x{ratio:.2f} by the FLOP ratio (torch flop counter on "
                        f"meta tensors) to the 25-frame 72x128 step ({full_flops / 1e12:.2f} TFLOP); 32x32 probe "

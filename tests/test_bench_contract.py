@@ -10,8 +10,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_reference_arm_prints_one_json_line():
+    # B200SVD_BENCH_CONTRACT_TEST: same code path on the reduced-width network (the real arm needs minutes of host time)
     p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
-                        "--warmup", "0"], capture_output=True, text=True, timeout=900, cwd=ROOT)
+                        "--warmup", "0"], capture_output=True, text=True, timeout=900, cwd=ROOT,
+                       env=dict(os.environ, B200SVD_BENCH_CONTRACT_TEST="1"))
     assert p.returncode == 0, p.stderr[-2000:]
     lines = [ln for ln in p.stdout.splitlines() if ln.strip()]
     assert len(lines) == 1, lines
