@@ -95,14 +95,15 @@ int encode_tmap_bf16_sw64(CUtensorMap* out, const void* gptr, int rank, const ui
 }
 
 int sm_count() {
-  static int n = 0;
-  if (n == 0) {
+  static int n[B200_MAX_DEVICES] = {};
+  const int slot = dev_slot();
+  if (n[slot] == 0) {
     int dev = 0;
     cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+    cudaDeviceGetAttribute(&n[slot], cudaDevAttrMultiProcessorCount, dev);
+    if (n[slot] <= 0) n[slot] = 148;
   }
-  return n;
+  return n[slot];
 }
 
 }  // namespace b200

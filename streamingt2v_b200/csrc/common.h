@@ -24,6 +24,16 @@ int encode_tmap_bf16_sw64(CUtensorMap* out, const void* gptr, int rank, const ui
 
 int sm_count();
 
+// Launch-attribute caches (cudaFuncSetAttribute results, occupancy queries) are kept PER DEVICE: function attributes
+// belong to a device's context, and one process may drive several GPUs (the reference does not, but the caches must not
+// silently assume it).  Index of the calling thread's current device, folded into [0, B200_MAX_DEVICES).
+constexpr int B200_MAX_DEVICES = 16;
+inline int dev_slot() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev & (B200_MAX_DEVICES - 1);
+}
+
 #define B200_CHECK_LAUNCH(name)                               \
   do {                                                        \
     cudaError_t e__ = cudaGetLastError();                     \

@@ -712,9 +712,11 @@ extern "C" int b200svd_flash_attn(const void* qkv, int64_t ldqkv, void* out, int
   // softmax warps; B200SVD_FA_POLY = 0..2 of every 8 score pairs take their exp2 on the FMA pipe (measured slower,
   // profiles/r02_bench_fa_*.txt)
   static int poly = -1;
+  static bool attr_set[B200_MAX_DEVICES] = {};
   const int ver = fa_variant();
   const int fast = ver == 4 ? 1 : 0, v5 = ver == 5 ? 1 : 0;
-  if (poly < 0) {
+  const int slot = dev_slot();
+  if (poly < 0 || !attr_set[slot]) {
     const char* ev = getenv("B200SVD_FA_POLY");
     poly = ev ? atoi(ev) : FA_POLY_DEFAULT;
     if (poly < 0 || poly > 2) poly = FA_POLY_DEFAULT;
@@ -732,6 +734,7 @@ extern "C" int b200svd_flash_attn(const void* qkv, int64_t ldqkv, void* out, int
       poly = -1;
       return cuda_fail(e, "cudaFuncSetAttribute(flash_attn)");
     }
+    attr_set[slot] = true;
   }
   FaParams p;
   p.out = reinterpret_cast<__nv_bfloat16*>(out);

@@ -825,11 +825,12 @@ static int launch(const b200svd_gemm_params* p, const CUtensorMap& tmA, const Ge
       if (encode_rows_view(&tmR32, p->res1, p->ld1, n_out, p->m_ext, p->out_rs, qbox, 32)) return 1;
     }
   }
-  static bool attr_set = false;
-  if (!attr_set) {
+  const int slot = dev_slot();
+  static bool attr_set[B200_MAX_DEVICES] = {};
+  if (!attr_set[slot]) {
     cudaError_t e = cudaFuncSetAttribute(mtgemm_kernel<BN, CL, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(mtgemm)");
-    attr_set = true;
+    attr_set[slot] = true;
   }
   const uint64_t m_tiles = (uint64_t)dd.m_tiles[0] * dd.m_tiles[1] * dd.m_tiles[2];
   const uint64_t total = (uint64_t)dd.n_tiles * (PAIR ? (m_tiles + 1) / 2 : m_tiles);  // (pair) tiles
@@ -838,7 +839,8 @@ static int launch(const b200svd_gemm_params* p, const CUtensorMap& tmA, const Ge
     return 1;
   }
   // CTAs, CTA pairs or CTA quads that can be co-resident (clusters must fit inside a GPC, so quads may not tile all SMs)
-  static int max_clusters = 0;
+  static int max_clusters_dev[B200_MAX_DEVICES] = {};
+  int& max_clusters = max_clusters_dev[slot];
   if (max_clusters == 0) {
     max_clusters = sm_count() / CL;
     if (CL > 1) {

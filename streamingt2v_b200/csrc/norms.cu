@@ -554,7 +554,8 @@ int b200svd_gn_stats_partials(const float* gn_part, const int32_t* gn_slot_sampl
   const int64_t chunks = (n_slots + GNP_SLOTS - 1) / GNP_SLOTS;
   dim3 grid((unsigned)chunks, (unsigned)n);
   const size_t smem = (size_t)2 * c * sizeof(float);
-  static size_t smem_set = 0;
+  static size_t smem_set_dev[B200_MAX_DEVICES] = {};
+  size_t& smem_set = smem_set_dev[dev_slot()];
   if (smem > 48 * 1024 && smem > smem_set) {
     cudaError_t e = cudaFuncSetAttribute(gn_stats_partials_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(gn_stats_partials)");
@@ -583,7 +584,8 @@ int b200svd_gn_stats(const void* x, int64_t ldx, int64_t n, int64_t p, int c, vo
   dim3 grid(chunks, (unsigned)n);
   const int rstep = threads / (c / 8);
   const size_t smem = (size_t)rstep * 2 * c * sizeof(float);
-  static size_t smem_set = 0;
+  static size_t smem_set_dev[B200_MAX_DEVICES] = {};
+  size_t& smem_set = smem_set_dev[dev_slot()];
   if (smem > 48 * 1024 && smem > smem_set) {
     cudaError_t e = cudaFuncSetAttribute(gn_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, "gn_stats smem attribute");

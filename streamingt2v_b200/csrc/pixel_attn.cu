@@ -205,11 +205,12 @@ extern "C" int b200svd_pixel_attn(const void* q, int64_t ldq, const void* k, int
   if (encode_pixel_view(&tmQ, q, ldq, C, b, s, lq)) return 1;
   if (encode_pixel_view(&tmK, k, ldk, C, b, s, lk)) return 1;
   if (encode_pixel_view(&tmV, v, ldv, C, b, s, lk)) return 1;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[B200_MAX_DEVICES] = {};
+  const int slot = dev_slot();
+  if (!attr_set[slot]) {
     cudaError_t e = cudaFuncSetAttribute(pixel_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PA_SMEM_BYTES);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(pixel_attn)");
-    attr_set = true;
+    attr_set[slot] = true;
   }
   PaParams p;
   p.out = reinterpret_cast<__nv_bfloat16*>(o);
