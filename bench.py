@@ -523,12 +523,14 @@ def run_ours(args):
                 v["frac_of_hbm_peak"] = round(v["gb_per_s"] / hbm_peak, 3)
 
     # ---------------- one whole chunk: 30 sampler steps + temporal VAE decode (rank 0, single GPU) ----------------
-    chunk = None
+    chunk = first_chunk = None
     if rank == 0 and world == 1 and not args.no_chunk:
         try:
             chunk = chunk_leg(model, cfg, dev, c, kw, T, h, w)
+            first_chunk = chunk_leg(model, cfg, dev, c, kw, T, h, w, first=True)
         except Exception as exc:
-            chunk = {"error": repr(exc)}
+            chunk = chunk or {"error": repr(exc)}
+            first_chunk = first_chunk or {"error": repr(exc)}
 
     # ---------------- the reference computation as eager PyTorch on this GPU (rank 0, single GPU) ----------------
     gpu_ref = None
@@ -568,6 +570,16 @@ def run_ours(args):
             line["replicas"] = replicas
         if chunk is not None:
             line["chunk"] = chunk
+            line["first_chunk"] = first_chunk
+            if "ms_per_chunk" in chunk and first_chunk and "ms_per_chunk" in first_chunk:
+                # 200 output frames = the first 25-frame chunk + 10 autoregressive chunks of 18 new frames (25 + 180 >= 200,
+                # inference_i2v.py:35, streaming_svd.py:347); conditioner, enhance stage and VFI are not part of this number
+                t200 = (first_chunk["ms_per_chunk"] + 10 * chunk["ms_per_chunk"]) * 1e-3
+                line["streamingsvd_stage_200_frames"] = {
+                    "seconds": t200, "frames_per_sec": 200.0 / t200,
+                    "what": "StreamingSVD stage of a 200-frame request on ONE GPU: first chunk (configs[1]) + 10 autoregressive "
+                            "chunks (configs[2]); sampler + VAE decode only — conditioner, I2VGen-XL enhance stage and EMA-VFI "
+                            "(BASELINE configs[3], [4]) are not built and not included"}
         if gpu_ref is not None:
             line["gpu_reference"] = gpu_ref
             if "ms_per_step" in gpu_ref:
@@ -582,7 +594,7 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def chunk_leg(model, cfg, dev, c, kw, T, h, w):
+def chunk_leg(model, cfg, dev, c, kw, T, h, w, first=False):
     """BASELINE configs[2], one autoregressive chunk: B200EulerEDMSampler (30 AlignYourSteps Euler steps, CFG 1.5->3)
     over the seam + decode_first_stage (temporal VAE decoder, groups of <= 8 frames) -> 25 frames at 576x1024, of
     which 18 are new video (the first 7 re-generate the conditioning frames, streaming_svd.py:347)."""
@@ -592,12 +604,18 @@ def chunk_leg(model, cfg, dev, c, kw, T, h, w):
     from streamingt2v_b200.vae import B200VaeDecoder
     vcfg = arch.VaeConfig()
     dec = B200VaeDecoder(vcfg, arch.synth_state_dict_device(arch.vae_decoder_param_shapes(vcfg), dev, 3), dev)
-    smp = B200EulerEDMSampler(num_steps=30, num_frames=T)
+    if first:
+        # BASELINE configs[1]: the plain SVD chunk that opens a request (StableVideoDiffusionPipeline, streaming_svd.py:390):
+        # 25 Euler steps on Karras sigmas, guidance 1.0 -> 3.0, no ControlNet / CAM (159.9 TFLOP per step)
+        smp = B200EulerEDMSampler(num_steps=25, num_frames=T, min_scale=1.0, max_scale=3.0, schedule="karras")
+    else:
+        smp = B200EulerEDMSampler(num_steps=30, num_frames=T)
+    n_steps = smp.num_steps
     cond = {k: v[T:].to(dev) for k, v in c.items()}
     uc = {"crossattn": torch.zeros_like(cond["crossattn"]), "concat": torch.zeros_like(cond["concat"]),
           "vector": cond["vector"].clone()}
     extra = dict(image_only_indicator=None, num_video_frames=T, batch_size=2, num_conditional_frames=7,
-                 ctrl_frames=kw["ctrl_frames"].to(dev))
+                 ctrl_frames=None if first else kw["ctrl_frames"].to(dev))
     noise = torch.randn((T, 4, h, w), generator=torch.Generator(device=dev).manual_seed(7), device=dev)
 
     def decode(z):
@@ -619,10 +637,12 @@ def chunk_leg(model, cfg, dev, c, kw, T, h, w):
     torch.cuda.synchronize()
     clocks = sampler.stop()
     ms_s, ms_d = ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])
-    kept = T - 7
-    return dict(workload="one StreamingSVD chunk: 30 Euler steps (CFG 2, ControlNet+CAM) + temporal VAE decode of 25 "
-                         "frames at 576x1024 (BASELINE configs[2] per-chunk unit)",
-                ms_per_chunk=ms_s + ms_d, sampler_ms=ms_s, sampler_ms_per_step=ms_s / 30, vae_decode_ms=ms_d,
+    kept = T if first else T - 7
+    return dict(workload=("first chunk of a request: 25 Euler steps on Karras sigmas (CFG 2, plain SVD UNet, no ControlNet / "
+                          "CAM) + temporal VAE decode of 25 frames at 576x1024 (BASELINE configs[1])") if first else
+                         ("one StreamingSVD chunk: 30 Euler steps (CFG 2, ControlNet+CAM) + temporal VAE decode of 25 "
+                          "frames at 576x1024 (BASELINE configs[2] per-chunk unit)"),
+                ms_per_chunk=ms_s + ms_d, sampler_ms=ms_s, sampler_ms_per_step=ms_s / n_steps, vae_decode_ms=ms_d,
                 vae_ms_per_frame=ms_d / T, frames_decoded=T, new_frames_per_chunk=kept,
                 stage_frames_per_sec=kept / ((ms_s + ms_d) * 1e-3), gpu_launches=ops.launches() - l0,
                 finite=bool(torch.isfinite(frames).all()), clocks=clocks,

@@ -257,6 +257,94 @@ def unet_param_shapes(cfg: UNetConfig, root: str = "") -> Dict[str, tuple]:
     return d
 
 
+def plain_unet_param_shapes(cfg: UNetConfig, root: str = "") -> Dict[str, tuple]:
+    """The UNet WITHOUT the CAM mergers: what the first chunk's plain SVD network holds (streaming_svd.py:390)."""
+    d = unet_param_shapes(cfg, root)
+    return {k: v for k, v in d.items() if "cross_attention_merger_" not in k}
+
+
+# --------------------------------------------------------------------------------------------------------------
+# diffusers weight layout of the first chunk
+# --------------------------------------------------------------------------------------------------------------
+_RES_MAP = (("in_layers.0", "spatial_res_block.norm1"), ("in_layers.2", "spatial_res_block.conv1"),
+            ("emb_layers.1", "spatial_res_block.time_emb_proj"), ("out_layers.0", "spatial_res_block.norm2"),
+            ("out_layers.3", "spatial_res_block.conv2"), ("skip_connection", "spatial_res_block.conv_shortcut"),
+            ("time_stack.in_layers.0", "temporal_res_block.norm1"), ("time_stack.in_layers.2", "temporal_res_block.conv1"),
+            ("time_stack.emb_layers.1", "temporal_res_block.time_emb_proj"),
+            ("time_stack.out_layers.0", "temporal_res_block.norm2"), ("time_stack.out_layers.3", "temporal_res_block.conv2"),
+            ("time_mixer", "time_mixer"))
+_ATTN_MAP = (("time_stack.0", "temporal_transformer_blocks.0"), ("time_pos_embed.0", "time_pos_embed.linear_1"),
+             ("time_pos_embed.2", "time_pos_embed.linear_2"))   # every other sub-module keeps its name
+
+
+def sgm_to_diffusers_svd_keys(cfg: UNetConfig) -> Dict[str, str]:
+    """SGM key -> key of diffusers' `UNetSpatioTemporalConditionModel.state_dict()` for the plain SVD UNet.
+
+    The first chunk of a request is produced by `StableVideoDiffusionPipeline` (reference
+    code/diffusion_trainer/streaming_svd.py:390, checkpoint in the diffusers layout, config.yaml:283-294): 25 of the
+    175 UNet evaluations of a 200-frame request.  Same architecture as `VideoUNet` minus the CAM mergers, so the same
+    kernels serve it once the names are translated.  The table restates the module correspondence of diffusers'
+    public SVD conversion (block order of openaimodel.UNetModel vs down/mid/up blocks; VideoResBlock =
+    SpatioTemporalResBlock{spatial_res_block, temporal_res_block, time_mixer}; SpatialVideoTransformer =
+    TransformerSpatioTemporalModel{transformer_blocks, temporal_transformer_blocks, time_pos_embed, time_mixer}).
+    diffusers is not installed offline: parity unpinned — `tests/test_arch.py` checks that the map is a bijection
+    onto the SGM grammar; a wrong name fails loudly at load time (missing key), never silently."""
+    plan = build_plan(cfg, "", decoder=True)
+    nrb = cfg.num_res_blocks
+    prefix: Dict[str, str] = {"time_embed.0": "time_embedding.linear_1", "time_embed.2": "time_embedding.linear_2",
+                              "label_emb.0.0": "add_embedding.linear_1", "label_emb.0.2": "add_embedding.linear_2",
+                              "input_blocks.0.0": "conv_in", "out.0": "conv_norm_out", "out.2": "conv_out",
+                              "middle_block.0": "mid_block.resnets.0", "middle_block.1": "mid_block.attentions.0",
+                              "middle_block.2": "mid_block.resnets.1"}
+    idx = 1
+    for level in range(len(cfg.channel_mult)):
+        for j in range(nrb):
+            prefix[f"input_blocks.{idx}.0"] = f"down_blocks.{level}.resnets.{j}"
+            prefix[f"input_blocks.{idx}.1"] = f"down_blocks.{level}.attentions.{j}"
+            idx += 1
+        if level != len(cfg.channel_mult) - 1:
+            prefix[f"input_blocks.{idx}.0.op"] = f"down_blocks.{level}.downsamplers.0.conv"
+            idx += 1
+    for oi, blk in enumerate(plan.output_blocks):
+        u, j = divmod(oi, nrb + 1)
+        for li, layer in enumerate(blk.layers):
+            if isinstance(layer, Res):
+                prefix[f"output_blocks.{oi}.{li}"] = f"up_blocks.{u}.resnets.{j}"
+            elif isinstance(layer, Attn):
+                prefix[f"output_blocks.{oi}.{li}"] = f"up_blocks.{u}.attentions.{j}"
+            elif isinstance(layer, Up):
+                prefix[f"output_blocks.{oi}.{li}.conv"] = f"up_blocks.{u}.upsamplers.0.conv"
+    out: Dict[str, str] = {}
+    for key in plain_unet_param_shapes(cfg):
+        best = max((p for p in prefix if key == p or key.startswith(p + ".")), key=len, default=None)
+        if best is None:
+            raise KeyError(f"no diffusers counterpart for {key}")
+        rest = key[len(best):].lstrip(".")
+        is_res = ".resnets." in prefix[best]
+        for a, b in (_RES_MAP if is_res else _ATTN_MAP if ".attentions." in prefix[best] else ()):
+            if rest == a or rest.startswith(a + "."):
+                rest = b + rest[len(a):]
+                break
+        out[key] = prefix[best] + ("." + rest if rest else "")
+    return out
+
+
+def from_diffusers_svd_state_dict(sd_diffusers: Dict[str, "torch.Tensor"], cfg: UNetConfig) -> Dict[str, "torch.Tensor"]:
+    """State dict of `UNetSpatioTemporalConditionModel` -> SGM-named state dict that B200Denoiser / the oracle load."""
+    m = sgm_to_diffusers_svd_keys(cfg)
+    missing = [d for d in m.values() if d not in sd_diffusers]
+    if missing:
+        raise KeyError(f"{len(missing)} keys missing in the diffusers state dict, e.g. {missing[:4]}")
+    shapes = plain_unet_param_shapes(cfg)
+    out = {}
+    for k, d in m.items():
+        t = sd_diffusers[d]
+        if tuple(t.shape) != tuple(shapes[k]):
+            raise ValueError(f"{d}: shape {tuple(t.shape)} != {shapes[k]} expected for {k}")
+        out[k] = t
+    return out
+
+
 def controlnet_param_shapes(cfg: UNetConfig, root: str = "") -> Dict[str, tuple]:
     """Name -> shape of ControlNet.state_dict() (ControlNet.from_unet, use_image_encoder_normalization)."""
     import dataclasses

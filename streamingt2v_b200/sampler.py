@@ -26,7 +26,16 @@ _GUIDED_KEYS = ("vector", "crossattn", "concat")  # guiders.py:91
 
 class B200EulerEDMSampler:
     def __init__(self, num_steps: int = 30, num_frames: int = 25, min_scale: float = 1.5, max_scale: float = 3.0,
-                 additional_cond_keys=(), cfg_parallel: bool = False):
+                 additional_cond_keys=(), cfg_parallel: bool = False, schedule: str = "ays",
+                 sigma_min: float = 0.002, sigma_max: float = 700.0, rho: float = 7.0):
+        if schedule not in ("ays", "karras"):
+            raise ValueError(schedule)
+        # "karras": the first chunk of a request is sampled by diffusers' StableVideoDiffusionPipeline
+        # (streaming_svd.py:390): EulerDiscreteScheduler with Karras sigmas 700 -> 0.002 (rho 7), 25 steps, v-prediction,
+        # continuous timesteps 0.25 ln(sigma), guidance 1.0 -> 3.0 over the frames — the same Euler / EDM arithmetic as
+        # the AlignYourSteps sampler of the later chunks with another noise schedule (restated from the published
+        # scheduler; diffusers is absent offline: parity unpinned)
+        self.schedule, self.sigma_min, self.sigma_max, self.rho = schedule, float(sigma_min), float(sigma_max), float(rho)
         self.num_steps = int(num_steps)
         self.num_frames = int(num_frames)
         self.min_scale, self.max_scale = float(min_scale), float(max_scale)
@@ -39,6 +48,10 @@ class B200EulerEDMSampler:
     # -- AlignYourSteps.get_sigmas + Discretization.__call__(do_append_zero=True) ---------------------------------
     def get_sigmas(self, n=None) -> np.ndarray:
         n = self.num_steps if n is None else int(n)
+        if self.schedule == "karras":
+            ramp = np.linspace(0.0, 1.0, n)
+            lo, hi = self.sigma_min ** (1.0 / self.rho), self.sigma_max ** (1.0 / self.rho)
+            return np.concatenate([(hi + ramp * (lo - hi)) ** self.rho, [0.0]])
         t = np.asarray(AYS_SCHEDULE, dtype=np.float64)
         ys = np.interp(np.linspace(0, 1, n), np.linspace(0, 1, len(t)), np.log(t[::-1]))
         return np.concatenate([np.exp(ys)[::-1], [0.0]])

@@ -50,6 +50,16 @@ class B200StreamingWrapper(nn.Module):
             cfg = dataclasses.replace(cfg, cond_embed_channels=tuple(chans))
         return cls(cfg, diffusion_model.state_dict(), sd_c, device)
 
+    @classmethod
+    def from_diffusers_svd(cls, unet: nn.Module, device="cuda:0", cfg: Optional[UNetConfig] = None):
+        """Build the plain SVD denoiser of the FIRST chunk from diffusers' `UNetSpatioTemporalConditionModel`
+        (`svd_pipeline.unet`, streaming_svd.py:62,390): its state dict is renamed to the SGM grammar
+        (arch.sgm_to_diffusers_svd_keys) and runs on the same kernels, without ControlNet / CAM.  Calls then pass
+        `ctrl_frames=None`."""
+        from . import arch
+        cfg = cfg or UNetConfig()
+        return cls(cfg, arch.from_diffusers_svd_state_dict(unet.state_dict(), cfg), None, device)
+
     def forward(self, x: torch.Tensor, t: torch.Tensor, c: dict, **kwargs):
         batch_size = kwargs.pop("batch_size")
         num_video_frames = kwargs.pop("num_video_frames")

@@ -88,3 +88,36 @@ def test_replica_plumbing_world2():
     assert res[0][1] == res[1][1] == [11.0, 5.0]
     assert res[0][2] + res[1][2] == list(range(7))
     assert dist_utils.aggregate_throughput(10, 2, 500.0) == 40.0
+
+
+def test_diffusers_svd_key_map_is_a_bijection_onto_the_sgm_grammar():
+    """First-chunk weights come in the diffusers layout (streaming_svd.py:390).  The translation table must cover
+    every tensor of the plain SVD UNet exactly once, keep shapes, and follow diffusers' block structure."""
+    import torch
+    from streamingt2v_b200 import arch
+    for cfg in (arch.UNetConfig(), arch.TINY):
+        m = arch.sgm_to_diffusers_svd_keys(cfg)
+        shapes = arch.plain_unet_param_shapes(cfg)
+        assert set(m) == set(shapes) and len(set(m.values())) == len(m)
+        assert not any("cross_attention_merger" in k for k in m)
+        tops = {v.split(".")[0] for v in m.values()}
+        assert tops == {"time_embedding", "add_embedding", "conv_in", "down_blocks", "mid_block", "up_blocks",
+                        "conv_norm_out", "conv_out"}
+        # structure: 4 down blocks with 2 resnets, attentions on the first 3; up block 0 has no attentions
+        assert m["input_blocks.11.0.in_layers.2.weight"] == "down_blocks.3.resnets.1.spatial_res_block.conv1.weight"
+        assert not any(v.startswith("down_blocks.3.attentions") or v.startswith("up_blocks.0.attentions") for v in m.values())
+        assert m["output_blocks.2.1.conv.weight"] == "up_blocks.0.upsamplers.0.conv.weight"
+        assert m["input_blocks.1.1.time_stack.0.attn1.to_q.weight"] == \
+            "down_blocks.0.attentions.0.temporal_transformer_blocks.0.attn1.to_q.weight"
+        assert m["input_blocks.1.1.time_pos_embed.2.bias"] == "down_blocks.0.attentions.0.time_pos_embed.linear_2.bias"
+    # round trip on the reduced network: rename a synthetic SGM state dict to diffusers names and back
+    cfg = arch.TINY
+    sd = {k: torch.full(s_, float(i % 7)) for i, (k, s_) in enumerate(sorted(arch.plain_unet_param_shapes(cfg).items()))}
+    m = arch.sgm_to_diffusers_svd_keys(cfg)
+    sd_diff = {m[k]: v for k, v in sd.items()}
+    back = arch.from_diffusers_svd_state_dict(sd_diff, cfg)
+    assert set(back) == set(sd) and all(torch.equal(back[k], sd[k]) for k in sd)
+    del sd_diff["conv_in.weight"]
+    import pytest
+    with pytest.raises(KeyError, match="missing"):
+        arch.from_diffusers_svd_state_dict(sd_diff, cfg)

@@ -114,3 +114,17 @@ def test_sampler_loop_gpu_matches_oracle(cuda_dev):
     ref = _oracle_loop(x.clone(), cond, uc, 6, T)
     # tanh on the GPU vs the CPU differs by a few ulp and is amplified by 1/sigma in the last steps
     assert (out.cpu() - ref).abs().max() <= 1e-4 * ref.abs().max()
+
+
+def test_karras_schedule_of_the_first_chunk():
+    """EulerDiscreteScheduler(use_karras_sigmas) as StableVideoDiffusionPipeline uses it for chunk 1: 25 sigmas from 700
+    to 0.002 with rho = 7, then 0 (published formula; diffusers absent: parity unpinned)."""
+    import numpy as np
+    from streamingt2v_b200.sampler import B200EulerEDMSampler
+    smp = B200EulerEDMSampler(num_steps=25, num_frames=25, min_scale=1.0, max_scale=3.0, schedule="karras")
+    sig = smp.get_sigmas()
+    assert sig.shape == (26,) and sig[-1] == 0.0
+    assert abs(sig[0] - 700.0) < 1e-9 and abs(sig[24] - 0.002) < 1e-12 and np.all(np.diff(sig) < 0)
+    i = 7
+    expect = (700.0 ** (1 / 7) + i / 24 * (0.002 ** (1 / 7) - 700.0 ** (1 / 7))) ** 7
+    assert abs(sig[i] - expect) < 1e-9 * expect
