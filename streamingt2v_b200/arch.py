@@ -518,3 +518,53 @@ def vae_decoder_param_shapes(cfg: VaeConfig) -> Dict[str, tuple]:
             d["conv_out.time_mix_conv.weight"] = (cout, cout, 3, 1, 1)
             d["conv_out.time_mix_conv.bias"] = (cout,)
     return d
+
+
+# --------------------------------------------------------------------------------------------------------------
+# SD-VAE encoder of the conditioner (AutoencoderKLModeOnly.encode -> Encoder + quant_conv -> mode; reference
+# code/models/svd/sgm/modules/diffusionmodules/model.py:487-601, models/autoencoder.py:454-473,602-615;
+# used per chunk by VideoPredictionEmbedderWithEncoder, encoders/modules.py:697-729) — SURVEY.md section 8 row f1
+# --------------------------------------------------------------------------------------------------------------
+def vae_encoder_plan(cfg: VaeConfig):
+    """[(kind, prefix, cin, cout)] in execution order (Encoder.forward, model.py:578-601)."""
+    plan = [("conv_in", "conv_in", 3, cfg.ch)]
+    block_in = cfg.ch
+    for i_level, mult in enumerate(cfg.ch_mult):
+        block_out = cfg.ch * mult
+        for i_block in range(cfg.num_res_blocks):
+            plan.append(("res", f"down.{i_level}.block.{i_block}", block_in, block_out))
+            block_in = block_out
+        if i_level != len(cfg.ch_mult) - 1:
+            plan.append(("down", f"down.{i_level}.downsample", block_in, block_in))
+    plan.append(("res", "mid.block_1", block_in, block_in))
+    plan.append(("attn", "mid.attn_1", block_in, block_in))
+    plan.append(("res", "mid.block_2", block_in, block_in))
+    plan.append(("out", "", block_in, 2 * cfg.z_channels))
+    return plan
+
+
+def vae_encoder_param_shapes(cfg: VaeConfig) -> Dict[str, tuple]:
+    """Name -> shape of `Encoder.state_dict()` plus the engine's `quant_conv` (autoencoder.py:454-458), the latter
+    under the key `quant_conv.*` as in the checkpoint (`first_stage_model.quant_conv`)."""
+    d: Dict[str, tuple] = {}
+    for kind, p, cin, cout in vae_encoder_plan(cfg):
+        if kind == "conv_in":
+            _conv(d, p, cin, cout)
+        elif kind == "res":
+            _norm(d, p + ".norm1", cin)
+            _conv(d, p + ".conv1", cin, cout)
+            _norm(d, p + ".norm2", cout)
+            _conv(d, p + ".conv2", cout, cout)
+            if cin != cout:
+                _conv(d, p + ".nin_shortcut", cin, cout, 1)
+        elif kind == "down":
+            _conv(d, p + ".conv", cin, cin)
+        elif kind == "attn":
+            _norm(d, p + ".norm", cin)
+            for n in ("q", "k", "v", "proj_out"):
+                _conv(d, f"{p}.{n}", cin, cin, 1)
+        elif kind == "out":
+            _norm(d, "norm_out", cin)
+            _conv(d, "conv_out", cin, cout)
+    _conv(d, "quant_conv", 2 * cfg.z_channels, 2 * cfg.z_channels, 1)
+    return d

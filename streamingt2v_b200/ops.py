@@ -280,9 +280,12 @@ def conv3x3(x, w, bias=None, *, out=None, **epi):
                         (64, b1, b2, b3, 1), w, Cout, Cc, taps, (W, H, N), (b1, b2, b3), (1, 2, 3), bias, out, epi)
 
 
-def conv3x3_s2(x, w, bias=None, *, out=None, **epi):
-    """Stride-2, pad-1 3x3 conv (Downsample.op, openaimodel.py:188-195).  x: [N, H, W, C] with even H, W.
-    The input is viewed as [N, H/2, 2, W/2, 2*C] so that every tap is a plain shifted TMA box."""
+def conv3x3_s2(x, w, bias=None, *, out=None, pad_after_only=False, **epi):
+    """Stride-2 3x3 conv.  x: [N, H, W, C] with even H, W.  The input is viewed as [N, H/2, 2, W/2, 2*C] so that every
+    tap is a plain shifted TMA box (out-of-range boxes are zero filled = the padding).
+    pad_after_only=False: pad 1 on every side (Downsample.op of the UNet, openaimodel.py:188-195): tap k reads input
+    row 2i + k - 1.  pad_after_only=True: pad (0,1,0,1) + padding-0 conv (Downsample of the autoencoder,
+    diffusionmodules/model.py:73-92): tap k reads input row 2i + k."""
     assert x.dtype == torch.bfloat16 and x.dim() == 4 and x.is_contiguous()
     N, H, W, Cc = x.shape
     assert H % 2 == 0 and W % 2 == 0
@@ -291,10 +294,12 @@ def conv3x3_s2(x, w, bias=None, *, out=None, **epi):
     assert w.shape == (9, Cout, Cc) and w.is_contiguous()
     b1, b2, b3 = pick_box(Wo, Ho, N)
     taps = []
+    # (offset in output rows, parity inside the row pair) of input row 2i + k - 1  /  2i + k
+    table = ((0, 0), (0, 1), (1, 0)) if pad_after_only else ((-1, 1), (0, 0), (0, 1))
     for kh in range(3):
-        dh, hp = ((-1, 1), (0, 0), (0, 1))[kh]
+        dh, hp = table[kh]
         for kw in range(3):
-            dw, wp = ((-1, 1), (0, 0), (0, 1))[kw]
+            dw, wp = table[kw]
             taps.append((wp * Cc, dw, hp, dh, 0))
     return _conv_common(x, (2 * Cc, Wo, 2, Ho, N),
                         (2 * Cc * 2, W * Cc * 2, 2 * W * Cc * 2, H * W * Cc * 2),

@@ -67,7 +67,11 @@ def _conv(x, w, stride, bias, out, epi):
     N, H, W, Cc = x.shape
     cout = w.shape[1]
     wt = w.float().reshape(3, 3, cout, Cc).permute(2, 3, 0, 1)
-    v = F.conv2d(x.float().permute(0, 3, 1, 2), wt, None, stride=stride, padding=1).permute(0, 2, 3, 1)
+    xin = x.float().permute(0, 3, 1, 2)
+    if epi.pop("pad_after_only", False):
+        v = F.conv2d(F.pad(xin, (0, 1, 0, 1)), wt, None, stride=stride).permute(0, 2, 3, 1)
+    else:
+        v = F.conv2d(xin, wt, None, stride=stride, padding=1).permute(0, 2, 3, 1)
     v = v.reshape(-1, cout)
     return _epilogue(v, v.shape[0], bias=bias, act=epi.get("act", ACT_NONE), fvec=epi.get("fvec"),
                      rows_per_frame=epi.get("rows_per_frame", 1), s_acc=epi.get("s_acc", 1.0), res1=epi.get("res1"),

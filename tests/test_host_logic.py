@@ -166,3 +166,22 @@ def test_batch_halves_equal_batch_one_forwards(patched_model):
                            batch_size=1, num_video_frames=T, ctrl_frames=kw["ctrl_frames"])
         assert half.shape == (T,) + tuple(ref.shape[1:])
         assert _rel(half, ref[sl]) < 3e-2, (r, _rel(half, ref[sl]))
+
+
+def test_vae_encoder_wiring(monkeypatch):
+    """SD-VAE encoder executor (B200VaeEncoder: conv_out and quant_conv folded, asymmetric-pad stride-2 convs) with the
+    CPU stand-in ops against the golden of the unmodified reference Encoder."""
+    import os
+
+    import numpy as np
+    from oracle.make_golden_vae_enc import make_image
+    from streamingt2v_b200 import arch, vae
+    monkeypatch.setattr(vae, "ops", fake_ops)
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "vae_enc_2_64x96.npz"))
+    n, H, W, seed = (int(v) for v in g["meta"])
+    cfg = arch.VaeConfig()
+    sd = arch.synth_state_dict(arch.vae_encoder_param_shapes(cfg), seed=seed)
+    out = vae.B200VaeEncoder(cfg, sd, "cpu").encode(make_image(n, H, W, seed))
+    ref = torch.from_numpy(g["out"])
+    assert out.shape == ref.shape == (n, 4, H // 8, W // 8)
+    assert _rel(out, ref) < 3e-2, _rel(out, ref)

@@ -44,3 +44,23 @@ def test_grammar_counts():
     nc = sum(int(np.prod(s)) for s in c.values())
     assert len(u) == 1571 and len(c) == 657
     assert abs(nu / 1e6 - 1593.5) < 0.1 and abs(nc / 1e6 - 673.0) < 0.1
+
+
+@pytest.mark.parametrize("name", ["vae_enc_2_64x96", "vae_enc_1_128x64"])
+def test_vae_encoder_oracle_matches_reference_golden(name):
+    """oracle/vae_encoder_oracle.py against the outputs of the unmodified reference Encoder (+ quant_conv, mode)."""
+    import os
+
+    import numpy as np
+    import torch
+    from oracle import vae_encoder_oracle as eorc
+    from oracle.make_golden_vae_enc import make_image
+    from streamingt2v_b200 import arch
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", f"{name}.npz"))
+    n, H, W, seed = (int(v) for v in g["meta"])
+    cfg = arch.VaeConfig()
+    sd = arch.synth_state_dict(arch.vae_encoder_param_shapes(cfg), seed=seed)
+    with torch.no_grad():
+        out = eorc.encode(sd, cfg, make_image(n, H, W, seed))
+    ref = torch.from_numpy(g["out"])
+    assert (out - ref).abs().max().item() <= 2e-4 * max(1.0, ref.abs().max().item())

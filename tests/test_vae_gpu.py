@@ -72,3 +72,36 @@ def test_attention_single_head(cuda_dev):
                                          v.float().reshape(n, 1, s, c)).reshape(n * s, c)
     err = (o.float() - ref).abs()
     assert (err <= 2e-2 + 2 ** -6 * ref.abs()).all(), err.max().item()
+
+
+@pytest.mark.parametrize("name", ["vae_enc_2_64x96", "vae_enc_1_128x64"])
+def test_vae_encode_vs_reference_golden(cuda_dev, name):
+    """B200VaeEncoder.encode == mode(quant_conv(Encoder(x))) of the unmodified reference (conditioner's SD-VAE encoder,
+    SURVEY.md section 8 row f1).  Same tolerance as the decoder: relative L2 <= 3e-2 overall and per block."""
+    from oracle import vae_encoder_oracle as eorc
+    from oracle.make_golden_vae_enc import make_image
+    from streamingt2v_b200 import arch
+    from streamingt2v_b200.vae import B200VaeEncoder
+    g = np.load(os.path.join(GOLDEN, f"{name}.npz"))
+    n, H, W, seed = (int(v) for v in g["meta"])
+    cfg = arch.VaeConfig()
+    sd = arch.synth_state_dict(arch.vae_encoder_param_shapes(cfg), seed=seed)
+    x = make_image(n, H, W, seed)
+    enc = B200VaeEncoder(cfg, sd, cuda_dev)
+    enc.debug_taps = {}
+    out = enc.encode(x.to(cuda_dev))
+    torch.cuda.synchronize()
+    out = out.cpu()
+    ref = torch.from_numpy(g["out"])
+    r = _rel(out, ref)
+    print(f"[{name}] vs REFERENCE golden: rel_l2={r:.4e} max_abs={(out - ref).abs().max():.3e}")
+    assert torch.isfinite(out).all() and out.shape == ref.shape
+    taps = {}
+    with torch.no_grad():
+        eorc.encode(sd, cfg, x, taps=taps)
+    for tname, (tt, nn_, hh, ww) in enc.debug_taps.items():
+        mine = tt.float().cpu().reshape(nn_, hh, ww, -1).permute(0, 3, 1, 2)
+        rr = _rel(mine, taps[tname])
+        assert rr < 3e-2, (tname, rr)
+    assert r < 3e-2
+    assert torch.equal(out, enc.encode(x.to(cuda_dev)).cpu()), "encode is not deterministic"
