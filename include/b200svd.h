@@ -201,6 +201,14 @@ int b200svd_ddim_blend_step(const float* noise, const float* lat, float* out, in
                             int lat_frames, int lat_start, int out_frames, int out_start, int offset, int cfg,
                             float guidance, float alpha_t, float alpha_prev, int v_pred, void* stream);
 
+/* ---- frames for the media container (on-device part) ---------------------------------
+ * float NCHW in [vmin, vmax] -> uint8 NHWC with the arithmetic of the reference's `torch2np`
+ * (code/lib/farancia/libimage/iimage.py:21-39; `IImage(chunk, vmin=0, vmax=255)` at utils/result_processor.py:24):
+ * out = uint8(255 * (clip(x, vmin, vmax) - vmin) / (vmax - vmin)), truncating.  The device->host copy of a chunk
+ * shrinks from 4 to 1 byte per sample. */
+int b200svd_frames_to_uint8(const float* x, void* out, int64_t n, int c, int64_t hw, float vmin, float vmax,
+                            void* stream);
+
 #ifdef __cplusplus
 }
 #endif

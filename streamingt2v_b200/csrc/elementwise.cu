@@ -375,9 +375,39 @@ __global__ void ddim_blend_step_kernel(const float* __restrict__ noise, const fl
   out[(c * out_frames + out_start + f) * hw + px] = sap * x0 + dir * eps;
 }
 
+// Frames for the media container: float NCHW in [vmin, vmax] -> uint8 NHWC, exactly the arithmetic of the reference's
+// torch2np (code/lib/farancia/libimage/iimage.py:21-39): 255 * (clip(x) - vmin) / (vmax - vmin), truncated to uint8.
+__global__ void frames_to_uint8_kernel(const float* __restrict__ x, uint8_t* __restrict__ out, int64_t n, int c,
+                                       int64_t hw, float vmin, float vmax) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // over (frame, pixel)
+  if (i >= n * hw) return;
+  const int64_t f = i / hw, px = i % hw;
+  for (int ch = 0; ch < c; ++ch) {
+    float v = x[(f * c + ch) * hw + px];
+    v = fminf(fmaxf(v, vmin), vmax);
+    v = 255.0f * (v - vmin) / (vmax - vmin);   // same operation order as the reference expression (IEEE division)
+    out[i * c + ch] = (uint8_t)v;               // float -> uint8 truncates toward zero, like torch's .to(torch.uint8)
+  }
+}
+
 }  // namespace b200
 
 extern "C" {
+
+int b200svd_frames_to_uint8(const float* x, void* out, int64_t n, int c, int64_t hw, float vmin, float vmax,
+                            void* stream) {
+  using namespace b200;
+  if (!(vmax > vmin) || c < 1 || c > 4) {
+    set_error("frames_to_uint8: need vmax > vmin and 1..4 channels");
+    return 1;
+  }
+  const int64_t tot = n * hw;
+  if (tot <= 0) return 0;
+  frames_to_uint8_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      x, reinterpret_cast<uint8_t*>(out), n, c, hw, vmin, vmax);
+  B200_CHECK_LAUNCH("frames_to_uint8");
+  return 0;
+}
 
 int b200svd_ddim_blend_step(const float* noise, const float* lat, float* out, int channels, int cs, int64_t hw,
                             int lat_frames, int lat_start, int out_frames, int out_start, int offset, int cfg,

@@ -584,6 +584,17 @@ def ddim_blend_step(noise, latents, out, *, lat_start, out_start, offset, guidan
     return out
 
 
+def frames_to_uint8(x, vmin=0.0, vmax=255.0):
+    """fp32 [F, C, H, W] in [vmin, vmax] -> uint8 [F, H, W, C] (the array the reference's IImage container holds,
+    lib/farancia/libimage/iimage.py:21-39)."""
+    assert x.dtype == torch.float32 and x.dim() == 4 and x.is_contiguous()
+    Fn, Cc, H, W = x.shape
+    out = torch.empty((Fn, H, W, Cc), dtype=torch.uint8, device=x.device)
+    _call("b200svd_frames_to_uint8", _ptr(x), _ptr(out), Fn, Cc, H * W, float(vmin), float(vmax), _stream(),
+          nbytes=5.0 * x.numel())
+    return out
+
+
 def attention_single_head(q, k, v, n, s):
     """softmax(q k^T / sqrt(C)) v per frame, one head of width C (VAE AttnBlock).  q, k, v: contiguous [(n s), C] bf16.
     Built from the tensor-core GEMM (scores in fp32), a row-softmax kernel and a transpose."""

@@ -140,3 +140,10 @@ class B200StreamingSVDStage:
             chunks.append(result[self.num_conditional_frames:])         # :347 keep all but the conditioning frames
         chunks = [convert_range(ch.to(torch.float32), [0, 255], [-1, 1]) for ch in chunks]
         return torch.cat([ch.to(chunks[0].device) for ch in chunks], dim=0)
+
+    def to_uint8_frames(self, video: torch.Tensor) -> torch.Tensor:
+        """[F,C,H,W] float in [0, 255] -> uint8 [F,H,W,C] ON THE DEVICE: the array the reference's IImage container
+        ends up holding after `result_processor.concat_chunks` (utils/result_processor.py:17-31,
+        lib/farancia/libimage/iimage.py:21-39), ready for a 1-byte-per-sample device->host copy."""
+        from . import ops
+        return ops.frames_to_uint8(video.to(self.device, torch.float32).contiguous(), 0.0, 255.0)

@@ -280,3 +280,8 @@ def ddim_blend_step(noise, latents, out, *, lat_start, out_start, offset, guidan
     res = math.sqrt(alpha_prev) * x0 + math.sqrt(1.0 - alpha_prev) * eps
     out[:, :, out_start + offset:out_start + cs] = res[:, :, offset:]
     return out
+
+
+def frames_to_uint8(x, vmin=0.0, vmax=255.0):
+    _count()
+    return (255 * (x.clip(vmin, vmax) - vmin) / (vmax - vmin)).permute(0, 2, 3, 1).to(torch.uint8).contiguous()

@@ -192,3 +192,22 @@ def test_glue(cuda_dev):
     mixed = F.layer_norm(F.conv1d(ctx, w, wb, padding=1), (1024,), lg, lb, 1e-5)
     ref = (ctx[:, :1] + mixed * F.silu(alpha))[:, 0]
     _check(o, ref, "apm_mix", rtol=2 ** -7, atol=1e-2)
+
+
+def test_frames_to_uint8_matches_reference_torch2np(cuda_dev):
+    """Bit-exact (integer output) against the expression of the reference's torch2np
+    (lib/farancia/libimage/iimage.py:33-36) on values that cover the clip edges and the golden video of the stage."""
+    import os
+
+    import numpy as np
+    from streamingt2v_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    x = (torch.rand(5, 3, 37, 53, generator=g) * 300.0 - 20.0)          # below 0 and above 255 included
+    x[0, 0, 0, :8] = torch.tensor([0.0, 255.0, 254.999, 0.999, 1.0, 127.5, -0.0, 255.001])
+    ref = (255 * (x.clip(0, 255) - 0) / (255 - 0)).permute(0, 2, 3, 1).to(torch.uint8)
+    out = ops.frames_to_uint8(x.to(cuda_dev), 0.0, 255.0)
+    torch.cuda.synchronize()
+    assert out.dtype == torch.uint8 and out.shape == ref.shape and torch.equal(out.cpu(), ref)
+    y = torch.rand(2, 3, 16, 24, generator=g) * 2.4 - 1.2                  # [-1, 1] range variant (IImage default)
+    ref2 = (255 * (y.clip(-1, 1) + 1) / 2).permute(0, 2, 3, 1).to(torch.uint8)
+    assert torch.equal(ops.frames_to_uint8(y.to(cuda_dev), -1.0, 1.0).cpu(), ref2)

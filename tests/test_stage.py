@@ -116,6 +116,15 @@ def test_stage_driver_matches_unmodified_reference_methods():
     assert tuple(calls[0]["ctrl_shape"]) == tuple(g["ctrl_shape"].tolist())
     assert np.allclose([c["ctrl_sum"] for c in calls], g["ctrl_sums"], rtol=1e-6, atol=1e-6)
     assert np.allclose([c["vec_sum"] for c in calls], g["vec_sums"], rtol=1e-6, atol=1e-6)
+    # the on-device uint8 conversion (host stand-in here) gives the container array directly
+    import fake_ops
+    from streamingt2v_b200 import ops as real_ops
+    saved = real_ops.frames_to_uint8
+    real_ops.frames_to_uint8 = fake_ops.frames_to_uint8
+    try:
+        assert np.array_equal(stage.to_uint8_frames(video).numpy(), g["video_u8"])
+    finally:
+        real_ops.frames_to_uint8 = saved
     # and the independent restatement (oracle/stage_oracle.py) agrees with the reference as well
     torch.manual_seed(seed)
     net2 = st.StubNetwork()
