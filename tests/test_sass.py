@@ -61,3 +61,22 @@ def test_attention_kernels_use_tcgen05(sass):
             assert "UTCHMMA" in body and "UTMALDG" in body, f"{name}: not on tcgen05 + TMA"
             assert "LDTM" in body and "STTM" in body, f"{name}: P/O should move through TMEM"
             assert "MUFU.EX2" in body
+
+
+def test_round2_epilogues_and_softmax_use_packed_math(sass):
+    """The specialised GEGLU / lean epilogues (mtgemm EPI = 1 / 2) and the single-pass softmax compute on packed fp32 pairs
+    (FFMA2 / FMUL2 / FADD2) and the softmax max on FMNMX3; the 320-wide 2-SM tile exists; the softmax warps re-split the
+    register file (setmaxnreg -> USETMAXREG)."""
+    geglu = {k: v for k, v in _of(sass, "mtgemm_kernel").items() if "ILi256ELi2ELi1E" in k or "ILi256ELi1ELi1E" in k}
+    assert len(geglu) == 2, sorted(geglu)
+    for name, body in geglu.items():
+        assert body.count("FFMA2") >= 100 and "FMUL2" in body and "FADD2" in body, f"{name}: GEGLU epilogue is not packed"
+    lean = {k: v for k, v in _of(sass, "mtgemm_kernel").items() if k.endswith("ELi2EEEv14CUtensorMap_stS1_S1_S1_S1_S1_S1_NS_7GemmDevE")}
+    assert len(lean) >= 6 and all("FFMA2" in v or "FADD2" in v for v in lean.values())
+    assert any("ILi320ELi2E" in k for k in _of(sass, "mtgemm_kernel")), "320-wide 2-SM tile missing"
+    fast = {k: v for k, v in _of(sass, "flash_attn_kernel").items() if "Lb1E" in k}
+    assert fast, "single-pass softmax instantiation missing"
+    for name, body in fast.items():
+        assert "FMNMX3" in body and "FFMA2" in body and "FADD2" in body, f"{name}: softmax is not on packed math"
+    for name, body in {**_of(sass, "flash_attn_kernel"), **_of(sass, "flash_attn5_kernel")}.items():
+        assert "USETMAXREG" in body, f"{name}: no setmaxnreg"
